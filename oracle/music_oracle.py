@@ -1,0 +1,179 @@
+"""CPU oracle (numpy, fp64) for gr-baz's MUSIC DOA block.  TEST INFRASTRUCTURE ONLY.
+
+This file is a restatement of the reference algorithm; it is *not* product code.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it, and there only as the checker.  The product path
+(``gr-baz_b200``) never routes through it.
+
+PARITY UNPINNED BY THE REFERENCE.  The reference ships no tests, golden vectors or
+fixtures for this block (``python/qa_baz.py:26-56`` and
+``lib/qa_baz.cc:32-41`` are empty stubs), and the reference itself cannot be built or
+imported here (GNU Radio, Boost, Armadillo, SWIG, Python 2 absent).  The arithmetic of
+the path lives in Armadillo (un-vendored, no version pinned:
+``CMakeLists-3.7.txt:195``, ``cmake/Modules/FindArmadillo.cmake:45-73``) on top of the
+system LAPACK (``eig_sym`` -> zheev/zheevd).  This restatement therefore follows the
+reference *source text* line by line and uses numpy's LAPACK ``zheevd`` binding
+(``numpy.linalg.eigh``) - the same routine family Armadillo dispatches to - for the
+eigendecomposition.  Our own golden vectors (``tests/golden``) are produced by this file.
+
+Reference lines restated (all under /root/reference):
+  lib/baz_music_doa.cc:72-161   work()
+  lib/baz_music_doa.cc:35-53    constructor checks
+  python/music_doa_helper.py:29-46,55-56   steering table
+  swig/baz_swig.i:564           complex128 -> complex64 rounding of the table
+"""
+from __future__ import annotations
+
+import numpy as np
+
+C_LIGHT = 299792458.0  # python/music_doa_helper.py:55
+
+
+# --------------------------------------------------------------------------------------
+# Steering table: python/music_doa_helper.py:29-46 (+ the SWIG c128->c64 rounding)
+# --------------------------------------------------------------------------------------
+def unit_vect(theta):
+    """python/music_doa_helper.py:29-30"""
+    return np.array([np.cos(theta), np.sin(theta)])
+
+
+def calculate_antenna_array_response_literal(antenna_array, angular_resolution, l):
+    """Literal restatement of python/music_doa_helper.py:32-46 (K*M Python loop, c128).
+
+    Returns a nested list [K][M] of Python complex, exactly what the helper hands to SWIG.
+    """
+    response = []
+    for step in range(0, angular_resolution):
+        angle = (step * 360.0 / angular_resolution) * (np.pi / 180.0)  # :36
+        response_step = []
+        for antenna in antenna_array:
+            phase_offset = np.inner(antenna, unit_vect(angle)) / l  # :40
+            antenna_response = np.exp(-1j * 2.0 * np.pi * phase_offset)  # :41
+            response_step += [antenna_response]
+        response += [response_step]
+    return response
+
+
+def scaled_antenna_array(array_spacing, antenna_array):
+    """python/music_doa_helper.py:56: positions = spacing * [x, y]."""
+    return [[array_spacing * x, array_spacing * y] for [x, y] in antenna_array]
+
+
+def steering_table_c64(antenna_array_scaled, angular_resolution, wavelength):
+    """Table as the C++ block stores it: [K][M] complex64 (swig/baz_swig.i:564 marshals
+    Python complex (c128) into std::vector<std::vector<gr_complex>>, i.e. rounds to c64)."""
+    resp = calculate_antenna_array_response_literal(antenna_array_scaled, angular_resolution, wavelength)
+    return np.asarray(resp, dtype=np.complex128).astype(np.complex64)
+
+
+# --------------------------------------------------------------------------------------
+# work(): lib/baz_music_doa.cc:72-161
+# --------------------------------------------------------------------------------------
+def check_params(m, n, nsamples, resolution, table=None):
+    """Constructor asserts, lib/baz_music_doa.cc:45-50.  n must also be >= 1 and < m
+    (grc/baz_music_doa.xml doc: "it is necessary that n<m"; m == n underflows
+    ``cols(0, m-n-1)`` at :93)."""
+    if not (m > 0 and 1 <= n < m):
+        raise ValueError("need m > 0 and 1 <= n < m")
+    if not (nsamples > 0 and nsamples % m == 0):
+        raise ValueError("nsamples must be a positive multiple of m")
+    if not resolution > 0:
+        raise ValueError("resolution must be > 0")
+    if table is not None:
+        if table.shape != (resolution, m):
+            raise ValueError("array_response must be [resolution][m]")
+
+
+def covariance(in_c64, m):
+    """:74-85.  in_c64: (nsamples,) complex64.  x(r, c) = in[c*m + r] (column-major reshape)."""
+    data = in_c64.astype(np.complex128)  # :75-77 widen
+    average_over = data.shape[0] // m  # :83
+    x = data.reshape(average_over, m).T  # :82-84 (m rows, average_over cols)
+    R = (x @ x.conj().T) / float(average_over)  # :85
+    return R
+
+
+def pick_top_n_literal(P, n, resolution):
+    """Literal restatement of the insertion loop, :95,129-141.  P: fp64 strengths."""
+    vDOAs = [(0.0, 0.0, -1)] * n  # (angle, strength, bin); bin is ours, for the index gate
+    for step in range(resolution):
+        strength = P[step]
+        for i in range(n):
+            if strength > vDOAs[i][1]:  # :132, strict, NaN never true
+                angle = float(step) * 360.0 / float(resolution)  # :134
+                vDOAs.insert(i, (angle, float(strength), step))  # :136
+                vDOAs.pop()  # :137
+                break
+    return vDOAs
+
+
+def pick_top_n(P, n, resolution):
+    """Vectorised equivalent of pick_top_n_literal: n largest strictly-positive (non-NaN)
+    values, ordered (value desc, bin asc); unfilled slots stay (0, 0, -1)."""
+    P = np.asarray(P, dtype=np.float64)
+    valid = np.nonzero(P > 0.0)[0]  # NaN > 0 is False
+    order = valid[np.lexsort((valid, -P[valid]))][:n]
+    out = [(float(k) * 360.0 / float(resolution), float(P[k]), int(k)) for k in order]
+    out += [(0.0, 0.0, -1)] * (n - len(out))
+    return out
+
+
+def work(in_c64, m, n, table_c64, want_spectrum=True, literal_pick=False, return_internals=False):
+    """One window through lib/baz_music_doa.cc:72-161.
+
+    in_c64   : (nsamples,) complex64, sample-interleaved antennas.
+    table_c64: (K, m) complex64 array response.
+    Returns dict with float32 'angles'[n], 'levels'[n], int32 'bins'[n] (ours: -1 = unfilled),
+    float32 'spectrum'[K] (the optional port 2) and fp64 'P'[K] (the pre-cast strengths).
+    """
+    in_c64 = np.ascontiguousarray(in_c64, dtype=np.complex64)
+    table_c64 = np.ascontiguousarray(table_c64, dtype=np.complex64)
+    K = table_c64.shape[0]
+    check_params(m, n, in_c64.shape[0], K, table_c64)
+
+    R = covariance(in_c64, m)
+    eigvals, eigvec = np.linalg.eigh(R)  # :88-90 ascending eigenvalues, eigenvectors in columns
+    G = eigvec[:, 0 : m - n]  # :93
+
+    a = table_c64.astype(np.complex128)  # :110-112 widen per step
+    v = a @ G.conj()  # row k = (G^H a_k)^T, :116/118
+    # arma::norm(v, 2) for complex: sqrt(sum_i |v_i|^2) with |.| = std::abs
+    nrm = np.sqrt(np.sum(np.abs(v) ** 2, axis=1))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        P = 1.0 / (nrm * nrm)  # 1.0 / pow(norm, 2)
+
+    pick = pick_top_n_literal if literal_pick else pick_top_n
+    doas = pick(P, n, K)
+    res = {
+        "angles": np.array([d[0] for d in doas], dtype=np.float32),  # :153 double -> float
+        "levels": np.array([d[1] for d in doas], dtype=np.float32),  # :154
+        "bins": np.array([d[2] for d in doas], dtype=np.int32),
+        "P": P,
+    }
+    if want_spectrum:
+        with np.errstate(over="ignore"):
+            res["spectrum"] = P.astype(np.float32)  # :121
+    if return_internals:
+        res["R"] = R
+        res["eigvals"] = eigvals
+        res["noise_projector"] = G @ G.conj().T  # phase-free
+    return res
+
+
+def work_batch(in_c64, m, n, table_c64, want_spectrum=False):
+    """W windows; in_c64: (W, nsamples).  Same per-window results as calling work() W times
+    (the block is stateless across windows)."""
+    in_c64 = np.asarray(in_c64)
+    W = in_c64.shape[0]
+    K = table_c64.shape[0]
+    angles = np.zeros((W, n), np.float32)
+    levels = np.zeros((W, n), np.float32)
+    bins = np.zeros((W, n), np.int32)
+    P = np.zeros((W, K), np.float64)
+    spec = np.zeros((W, K), np.float32) if want_spectrum else None
+    for w in range(W):
+        r = work(in_c64[w], m, n, table_c64, want_spectrum=want_spectrum)
+        angles[w], levels[w], bins[w], P[w] = r["angles"], r["levels"], r["bins"], r["P"]
+        if want_spectrum:
+            spec[w] = r["spectrum"]
+    return {"angles": angles, "levels": levels, "bins": bins, "P": P, "spectrum": spec}
