@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py - MUSIC DOA windows/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl ours|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (covariance -> Hermitian eig -> pseudospectrum -> peak
+pick) over one batch of synthetic windows per GPU: BASELINE.json configs[1] = M=4 antennas,
+4096-snapshot windows, 3600-angle grid, 10 000 windows (1.31 GB, larger than the 126 MB L2,
+so every step streams from HBM).
+
+  value     windows/s, whole job, inputs resident in HBM, device-timed (CUDA events on the
+            launch stream), max over ranks.
+  e2e       same metric through the reference-facing block API (music_doa.work -> C ABI
+            process_host) with pinned HOST buffers: H2D of the windows and D2H of the results
+            are inside the timed region.
+  roofline  the dominant (HBM-touching) kernel: K1 covariance; algorithmic bytes per window
+            (8*M*N + 8*n + 4*n) x windows per launch / its measured duration.
+  cpu_baseline  the C oracle (a port of the reference's work(); the reference itself needs GNU
+            Radio + Armadillo and cannot be built here) timed on the host cores.
+  --impl reference  times that same CPU port with all host threads (the reference arm).
+
+Multi-GPU: windows shard round-robin (w -> GPU w mod G); weak scaling (each GPU
+keeps its 10 000 windows/step); the only collective is an NCCL all-gather of the int32 peak
+bins, inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from gr_baz_b200 import synth  # noqa: E402
+from gr_baz_b200.music_doa_helper import calculate_antenna_array_response  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config index (1-based, default 2)")
+    ap.add_argument("--windows", type=int, default=0, help="windows per step per GPU (default: config's, capped by memory)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(cfg_id, windows_override=0):
+    cfg = synth.config(cfg_id)
+    W = windows_override or min(cfg["windows"], {2: 10000, 3: 4096, 4: 8192, 5: 4096}.get(cfg_id, 10000))
+    return cfg, W
+
+
+def bytes_per_window(cfg):
+    return 8 * cfg["m"] * cfg["snapshots"] + 8 * cfg["n"] + 4 * cfg["n"]
+
+
+def table_for(cfg):
+    arr = [[synth.SPACING * x, synth.SPACING * y] for x, y in cfg["antenna_array"]]
+    resp = calculate_antenna_array_response(arr, cfg["resolution"], synth.C_LIGHT / synth.FREQUENCY)
+    return resp, np.asarray(resp, dtype=np.complex128).astype(np.complex64)
+
+
+def metric_name(cfg):
+    return "MUSIC windows/sec (M=%d ant x %d snap x %d angle)" % (cfg["m"], cfg["snapshots"], cfg["resolution"])
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(pw))}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_port_throughput(cfg, table_c64, seed, budget_s, threads):
+    """windows/s of the C oracle (port of the reference's work()) on `threads` host threads over
+    a bounded sample of the same synthetic stream.  Returns (value, nwindows, seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import c_oracle
+
+    c_oracle.lib()
+    m, n = cfg["m"], cfg["n"]
+    x0 = synth.gen_windows_numpy(cfg, seed, 0, 8)
+    t = time.perf_counter()
+    c_oracle.work_batch(x0, m, n, table_c64, want_P=False)
+    per = (time.perf_counter() - t) / 8
+    S = int(max(threads * 4, min(4096, budget_s * threads / per)))
+    S = (S // threads) * threads
+    x = synth.gen_windows_numpy(cfg, seed, 0, S)
+    parts = np.array_split(np.arange(S), threads)
+
+    def job(idx):
+        return c_oracle.work_batch(x[idx[0]:idx[-1] + 1], m, n, table_c64, want_P=False)["bins"]
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(job, parts))  # warm-up
+        t = time.perf_counter()
+        list(ex.map(job, parts))
+        dt = time.perf_counter() - t
+    return S / dt, S, dt, per
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg, W = workload(args.config, args.windows)
+    _, table = table_for(cfg)
+    seed = synth.BASE_SEED + args.config
+    threads = host_threads()
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import c_oracle
+
+    c_oracle.lib()
+    m, n = cfg["m"], cfg["n"]
+    x0 = synth.gen_windows_numpy(cfg, seed, 0, 8)
+    t = time.perf_counter()
+    c_oracle.work_batch(x0, m, n, table, want_P=False)
+    per = (time.perf_counter() - t) / 8
+    total = args.steps + args.warmup
+    S = int(max(threads, min(W, (90.0 / total) * threads / per)))  # whole run ~<= 1.5 min
+    S = max(threads, (S // threads) * threads)
+    x = synth.gen_windows_numpy(cfg, seed, 0, S)
+    parts = np.array_split(np.arange(S), threads)
+
+    def job(idx):
+        return c_oracle.work_batch(x[idx[0]:idx[-1] + 1], m, n, table, want_P=False)["bins"]
+
+    with ThreadPoolExecutor(threads) as ex:
+        for _ in range(args.warmup):
+            list(ex.map(job, parts))
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            list(ex.map(job, parts))
+        dt = time.perf_counter() - t
+    value = S * args.steps / dt
+    sample = "%d windows/step of the config-%d stream (first %d of %d), %d host threads, C port -O3" % (S, args.config, S, W, threads)
+    line = {
+        "impl": "reference", "metric": metric_name(cfg), "value": value, "unit": "windows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, args.config, W), "sample_windows_per_step": S},
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(cfg, cfg_id, W):
+    return "BASELINE configs[%d]: M=%d, %d-snapshot windows, %d-angle grid, n=%d, %d windows/step/GPU" % (
+        cfg_id - 1, cfg["m"], cfg["snapshots"], cfg["resolution"], cfg["n"], W)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from gr_baz_b200.music_doa import music_doa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, W = workload(args.config, args.windows)
+    resp, table = table_for(cfg)
+    seed = synth.BASE_SEED + args.config
+    n, K = cfg["n"], cfg["resolution"]
+    G = world
+
+    # this rank's shard of the global stream: windows w = i*G + rank  (round-robin)
+    blk = music_doa(cfg["m"], n, cfg["nsamples"], resp, K, device=local)
+    d_in = torch.empty((W, cfg["nsamples"] * 2), dtype=torch.float32, device=dev)
+    widx = np.arange(W, dtype=np.int64) * G + rank
+    synth.gen_windows_torch(cfg, seed, 0, W, dev, out=d_in, indices=widx)
+    d_ang = torch.empty((W, n), dtype=torch.float32, device=dev)
+    d_lvl = torch.empty((W, n), dtype=torch.float32, device=dev)
+    d_bins = torch.empty((W, n), dtype=torch.int32, device=dev)
+    d_all = torch.empty((G, W, n), dtype=torch.int32, device=dev) if G > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step():
+        blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(),
+                           stream=stream.cuda_stream)
+        if G > 1:
+            dist.all_gather_into_tensor(d_all.view(-1), d_bins.view(-1))  # gathered[r][i] <-> w = i*G + r
+
+    def sync_all():
+        if G > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = blk.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = blk.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    if G > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    value = W * G * args.steps / (ms * 1e-3)
+
+    # sanity: the result of the timed work is a real answer (mirror-folded true bins at 20 dB)
+    bins_h = d_bins.cpu().numpy()
+    ok_frac = None
+    if rank == 0 and not cfg.get("fixed_sources"):
+        tb = synth.true_bins(cfg, seed, indices=widx)[:, 0]
+        if cfg["geometry"] == "ula_x":
+            tb = np.minimum(tb, (K - tb) % K)
+        ok_frac = float(np.mean(np.abs(bins_h[:, 0] - tb) <= 2))
+
+    # ---- roofline leg: stage timing of the same step (separate, untimed passes) -------------
+    roof = None
+    stages = None
+    if rank == 0:
+        blk.set_stage_timing(True)
+        reps = 5
+        for _ in range(reps):
+            blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(),
+                               stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        ms4, chunks = blk.stage_times_ms()
+        blk.set_stage_timing(False)
+        cov_ms = ms4[0] / reps
+        stages = {"cov_ms": cov_ms, "eig_ms": ms4[1] / reps, "scan_ms": ms4[2] / reps, "topn_ms": ms4[3] / reps,
+                  "launches_per_step": chunks // reps}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = bytes_per_window(cfg) * W / (cov_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("config%d" % args.config)
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "K1 covariance (cov_tile_kernel)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if peaks else "fallback 6650 GB/s, of fallback",
+                "traffic": traffic, "bytes_per_window": bytes_per_window(cfg), "windows_per_launch": W,
+                "whole_step_frac": (bytes_per_window(cfg) * value / G / 1e9) / peak}
+
+    # ---- e2e: block API with pinned host buffers (H2D + D2H inside the timed region) --------
+    e2e = None
+    if not args.no_e2e:
+        We = min(W, 4096)
+        h_in = torch.empty((We, cfg["nsamples"] * 2), dtype=torch.float32).pin_memory()
+        h_in.copy_(d_in[:We].cpu())
+        h_ang = torch.empty((We, n), dtype=torch.float32).pin_memory()
+        h_lvl = torch.empty((We, n), dtype=torch.float32).pin_memory()
+        x_np = h_in.numpy().view(np.complex64)
+        a_np, l_np = h_ang.numpy(), h_lvl.numpy()
+        esteps = max(3, min(args.steps, 10))
+        for _ in range(3):
+            blk.work(We, [x_np], [a_np, l_np])
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            blk.work(We, [x_np], [a_np, l_np])  # synchronous: returns when results are in host memory
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if G > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": We * G * esteps / dt, "unit": "windows/s",
+               "h2d_bytes_per_step": int(We * cfg["nsamples"] * 8),
+               "d2h_bytes_per_step": int(We * n * 4 * 3), "windows_per_step": We, "steps": esteps,
+               "api": "music_doa.work() -> music_b200_process_host (pinned host buffers)"}
+        assert np.array_equal(blk.last_bins(), bins_h[:We]), "host path and device path disagree"
+
+    cpu = None
+    if rank == 0 and G == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        v, S, dt, per = cpu_port_throughput(cfg, table, seed, budget_s=12.0, threads=threads)
+        cpu = {"value": v, "unit": "windows/s", "cores": threads, "kind": "port",
+               "sample": "first %d windows of the same synthetic stream, %.1f s, C port of work() (-O3 -DNDEBUG)" % (S, dt),
+               "value_1core": 1.0 / per}
+
+    if rank == 0:
+        line = {
+            "metric": metric_name(cfg), "value": value, "unit": "windows/s", "n_gpus": G, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, args.config, W), "windows_per_step": W * G,
+                       "l2": "inputs %.2f GB/step/GPU > 126 MB L2 (no flush needed)" % (W * cfg["nsamples"] * 8 / 1e9),
+                       "sharding": "round-robin w mod G, NCCL all-gather of int32 peak bins" if G > 1 else "single GPU",
+                       "snr_db": cfg["snr_db"], "geometry": cfg["geometry"]},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "stages": stages, "sanity_bins_within_2_of_truth": ok_frac,
+        }
+        print(json.dumps(line))
+    blk.close()
+    if G > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,77 @@
+"""ctypes binding of the C ABI in include/music_b200.h (libmusic_b200.so).
+
+This is the stand-in for the SWIG layer of the reference (swig/baz_swig.i:560-574): SWIG is
+not available in this image, so the Python mirror of ``baz.music_doa`` talks to the same
+C ABI that lib/baz_music_doa.cc (the GNU Radio block) calls.  There is no fallback: if the
+library is missing or no sm_100 device is present, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+_lib = None
+
+OK, EINVAL, ECUDA, ENODEVICE, ENOMEM = 0, -1, -2, -3, -4
+
+
+class MusicB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("music_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load libmusic_b200.so (must have been built by __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError(
+                "CUDA library %s is missing - run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                "there is no CPU fallback" % path)
+        L = ctypes.CDLL(path)
+        vp, u32, fp = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p
+        L.music_b200_version.restype = ctypes.c_int
+        L.music_b200_create.argtypes = [ctypes.POINTER(vp), u32, u32, u32, u32, fp, ctypes.c_int]
+        L.music_b200_create.restype = ctypes.c_int
+        L.music_b200_set_table.argtypes = [vp, fp]
+        L.music_b200_set_table.restype = ctypes.c_int
+        L.music_b200_process_host.argtypes = [vp, fp, u32, fp, fp, fp, fp]
+        L.music_b200_process_host.restype = ctypes.c_int
+        L.music_b200_process_device.argtypes = [vp, fp, u32, fp, fp, fp, fp, vp]
+        L.music_b200_process_device.restype = ctypes.c_int
+        L.music_b200_process_device_ex.argtypes = [vp, fp, u32, fp, fp, fp, fp, fp, fp, fp, vp]
+        L.music_b200_process_device_ex.restype = ctypes.c_int
+        L.music_b200_launch_count.argtypes = [vp]
+        L.music_b200_launch_count.restype = ctypes.c_uint64
+        L.music_b200_set_stage_timing.argtypes = [vp, ctypes.c_int]
+        L.music_b200_set_stage_timing.restype = ctypes.c_int
+        L.music_b200_get_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+        L.music_b200_get_stage_times.restype = ctypes.c_int
+        L.music_b200_last_error.argtypes = [vp]
+        L.music_b200_last_error.restype = ctypes.c_char_p
+        L.music_b200_destroy.argtypes = [vp]
+        L.music_b200_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+EXPORTS = [
+    "music_b200_version", "music_b200_create", "music_b200_set_table", "music_b200_process_host",
+    "music_b200_process_device", "music_b200_process_device_ex", "music_b200_launch_count",
+    "music_b200_set_stage_timing", "music_b200_get_stage_times",
+    "music_b200_last_error", "music_b200_destroy",
+]
+
+
+def check(rc, handle=None):
+    if rc != OK:
+        msg = load().music_b200_last_error(handle)
+        raise MusicB200Error(rc, msg.decode() if msg else "?")

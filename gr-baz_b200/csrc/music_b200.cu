@@ -1,0 +1,492 @@
+// music_b200.cu - C-ABI shim (include/music_b200.h) over the sm_100a MUSIC DOA kernels.
+//
+// Host-side responsibilities only: argument checks (the reference's constructor asserts,
+// /root/reference/lib/baz_music_doa.cc:45-50, made real), device buffers, the steering-table
+// double buffer (set_array_response semantics, :60-70), chunking and host<->device staging.
+// No CPU compute path exists here: without an sm_100 device create() fails.
+#include "../../include/music_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "music_kernels.cuh"
+
+using namespace music;
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+struct DeviceTable {
+    float *c64 = nullptr;   // [K][M] (re, im)
+    double *soa = nullptr;  // [ntiles][2M+1][TILE]
+};
+
+}  // namespace
+
+struct music_b200 {
+    uint32_t m = 0, n = 0, nsamples = 0, K = 0, N = 0;
+    int device = 0;
+    int sm_count = 0;
+    std::mutex mutex;        // serialises process_*() and set_table(), like d_mutex (:67, :101)
+    std::string error;
+    std::atomic<uint64_t> launches{0};
+
+    DeviceTable table[2];
+    int cur_table = 0;
+
+    // device workspace, sized for `cap_windows`
+    uint32_t cap_windows = 0;
+    double *d_R = nullptr, *d_evals = nullptr, *d_Vt = nullptr, *d_P64 = nullptr;
+    bool p64_alloc = false;
+    bool ws_busy = false;
+    // optional per-stage timing (bench.py's roofline leg): events around K1/K2/K3/top-n per chunk
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;   // 5 events per timed chunk
+    size_t tev_used = 0;    // done[0] marks the end of the last process_device() on its stream
+
+    // host path staging
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    float *d_in[2] = {nullptr, nullptr};
+    float *d_ang[2] = {nullptr, nullptr}, *d_lvl[2] = {nullptr, nullptr}, *d_spec[2] = {nullptr, nullptr};
+    int32_t *d_bins[2] = {nullptr, nullptr};
+    uint32_t host_chunk = 0;
+    bool host_spec_alloc = false;
+};
+
+namespace {
+
+int fail(music_b200 *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) {
+        h->error = buf;
+    } else {
+        std::lock_guard<std::mutex> g(g_err_mutex);
+        g_create_error = buf;
+    }
+    return code;
+}
+
+#define CU(h, expr)                                                                             \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail((h), e_ == cudaErrorMemoryAllocation ? MUSIC_B200_ENOMEM : MUSIC_B200_ECUDA, \
+                        "%s failed: %s", #expr, cudaGetErrorString(e_));                        \
+    } while (0)
+
+size_t soa_doubles(uint32_t K, uint32_t M) { return (size_t)((K + TILE - 1) / TILE) * (2 * M + 1) * TILE; }
+
+int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t st)
+{
+    DeviceTable &t = h->table[slot];
+    CU(h, cudaMemcpyAsync(t.c64, table_c64, (size_t)h->K * h->m * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    const int ntiles = (h->K + TILE - 1) / TILE;
+    prep_table_kernel<<<ntiles, TILE, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.soa, (int)h->K, (int)h->m);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(st));
+    return MUSIC_B200_OK;
+}
+
+// Chunk size (windows) bounding the fp64 workspace to ~1 GiB.
+uint32_t pick_chunk(const music_b200 *h, bool need_p64)
+{
+    const size_t per_win = (size_t)h->m * h->m * 2 * 8 * 2 + h->m * 8 + (need_p64 ? (size_t)h->K * 8 : 0);
+    size_t c = ((size_t)1 << 30) / per_win;
+    c = std::max<size_t>(SCAN_B, std::min<size_t>(c, 1u << 20));
+    return (uint32_t)(c / SCAN_B * SCAN_B);
+}
+
+int ensure_workspace(music_b200 *h, uint32_t windows, bool need_p64)
+{
+    if (windows > h->cap_windows || (need_p64 && !h->p64_alloc)) {
+        const uint32_t cap = std::max(windows, h->cap_windows);
+        cudaFree(h->d_R); cudaFree(h->d_evals); cudaFree(h->d_Vt); cudaFree(h->d_P64);
+        h->d_R = h->d_evals = h->d_Vt = h->d_P64 = nullptr;
+        h->cap_windows = 0; h->p64_alloc = false;
+        const size_t mm = (size_t)h->m * h->m * 2;
+        CU(h, cudaMalloc(&h->d_R, cap * mm * sizeof(double)));
+        CU(h, cudaMalloc(&h->d_Vt, cap * mm * sizeof(double)));
+        CU(h, cudaMalloc(&h->d_evals, (size_t)cap * h->m * sizeof(double)));
+        if (need_p64) {
+            CU(h, cudaMalloc(&h->d_P64, (size_t)cap * h->K * sizeof(double)));
+            h->p64_alloc = true;
+        }
+        h->cap_windows = cap;
+    }
+    return MUSIC_B200_OK;
+}
+
+template <int MT>
+void launch_scan(music_b200 *h, const double *soa, uint32_t W, bool argmax, bool p64, bool spec, PeakOut po,
+                 float *d_spec, double *d_p64, cudaStream_t st)
+{
+    const int grid = (W + SCAN_B - 1) / SCAN_B;
+    const size_t smem = (size_t)SCAN_B * h->m * h->m * 2 * sizeof(double);
+#define SCAN_CASE(A, P, S)                                                                              \
+    if (argmax == A && p64 == P && spec == S)                                                           \
+        scan_kernel<MT, A, P, S><<<grid, TILE, smem, st>>>(soa, h->d_Vt, (int)h->m, (int)h->n, (int)h->K, \
+                                                           (int)W, po, d_spec, d_p64);
+    SCAN_CASE(true, false, false)
+    SCAN_CASE(true, false, true)
+    SCAN_CASE(true, true, false)
+    SCAN_CASE(true, true, true)
+    SCAN_CASE(false, true, false)
+    SCAN_CASE(false, true, true)
+#undef SCAN_CASE
+    h->launches++;
+}
+
+cudaEvent_t *timing_events(music_b200 *h)
+{
+    if (!h->timing) return nullptr;
+    if (h->tev_used + 5 > h->tev.size()) {
+        for (int i = 0; i < 5; ++i) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            h->tev.push_back(e);
+        }
+    }
+    cudaEvent_t *p = h->tev.data() + h->tev_used;
+    h->tev_used += 5;
+    return p;
+}
+
+// One chunk (<= cap_windows) entirely on `st`.
+int run_chunk(music_b200 *h, const float *d_in, uint32_t W, float *d_ang, float *d_lvl, float *d_spec,
+              int32_t *d_bins, double *d_P64_out, double *d_R_out, double *d_ev_out, cudaStream_t st)
+{
+    const int M = (int)h->m, N = (int)h->N;
+    const double *soa = h->table[h->cur_table].soa;
+    cudaEvent_t *tev = timing_events(h);
+    if (tev) cudaEventRecord(tev[0], st);
+    // K1 covariance
+    if (M % 4 == 0) {
+        const int T = M / 4;
+        const int wpb = 8;
+        {
+            const long long items = (long long)W * T;
+            cov_tile_kernel<false><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, h->d_R, (int)W, N, M);
+            h->launches++;
+        }
+        if (T > 1) {
+            const long long items = (long long)W * (T * (T - 1) / 2);
+            cov_tile_kernel<true><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, h->d_R, (int)W, N, M);
+            h->launches++;
+        }
+    } else {
+        const int E = M * (M + 1) / 2;
+        const int S = 256 / E;
+        cov_generic_kernel<<<W, 256, (size_t)S * E * 2 * sizeof(double), st>>>(d_in, h->d_R, (int)W, N, M);
+        h->launches++;
+    }
+    if (tev) cudaEventRecord(tev[1], st);
+    // K2 eigendecomposition
+    {
+        const int grid = (W + 127) / 128;
+        switch (M) {
+        case 4: eig_kernel<4, true><<<grid, 128, 0, st>>>(h->d_R, h->d_evals, h->d_Vt, M, (int)W); break;
+        default:
+            if (M <= 8) eig_kernel<8, false><<<grid, 128, 0, st>>>(h->d_R, h->d_evals, h->d_Vt, M, (int)W);
+            else eig_kernel<MAXM, false><<<grid, 128, 0, st>>>(h->d_R, h->d_evals, h->d_Vt, M, (int)W);
+            break;
+        }
+        h->launches++;
+    }
+    if (tev) cudaEventRecord(tev[2], st);
+    // K3 scan (+ top-n)
+    const bool argmax = (h->n == 1);
+    const bool need_p64 = !argmax || d_P64_out != nullptr;
+    double *p64 = d_P64_out ? d_P64_out : h->d_P64;
+    PeakOut po{d_ang, d_lvl, d_bins};
+    switch (M) {
+    case 4: launch_scan<4>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+    case 8: launch_scan<8>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+    case 16: launch_scan<16>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+    default: launch_scan<0>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+    }
+    if (tev) cudaEventRecord(tev[3], st);
+    if (!argmax) {
+        topn_kernel<<<(W + 7) / 8, 256, 0, st>>>(p64, (int)h->n, (int)h->K, (int)W, po);
+        h->launches++;
+    }
+    if (tev) cudaEventRecord(tev[4], st);
+    if (d_R_out)
+        CU(h, cudaMemcpyAsync(d_R_out, h->d_R, (size_t)W * M * M * 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (d_ev_out)
+        CU(h, cudaMemcpyAsync(d_ev_out, h->d_evals, (size_t)W * M * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaGetLastError());
+    return MUSIC_B200_OK;
+}
+
+int process_device_locked(music_b200 *h, const float *d_in, uint32_t nwindows, float *d_ang, float *d_lvl,
+                          float *d_spec, int32_t *d_bins, double *d_P64, double *d_R, double *d_ev,
+                          cudaStream_t st)
+{
+    if (nwindows == 0) return MUSIC_B200_OK;
+    if (!d_in || !d_ang) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 and d_angles must not be NULL");
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 must be 16-byte aligned");
+    const bool internal_p64 = (h->n != 1) && !d_P64;
+    const uint32_t chunk = pick_chunk(h, internal_p64);
+    int rc = ensure_workspace(h, std::min(chunk, (nwindows + SCAN_B - 1) / SCAN_B * SCAN_B), internal_p64);
+    if (rc) return rc;
+    // The fp64 workspace is per handle: order this call after the previous one even if the
+    // caller switched streams.
+    if (h->ws_busy) CU(h, cudaStreamWaitEvent(st, h->done[0], 0));
+    for (uint32_t w0 = 0; w0 < nwindows; w0 += chunk) {
+        const uint32_t W = std::min(chunk, nwindows - w0);
+        rc = run_chunk(h, d_in + (size_t)w0 * h->nsamples * 2, W, d_ang + (size_t)w0 * h->n,
+                       d_lvl ? d_lvl + (size_t)w0 * h->n : nullptr, d_spec ? d_spec + (size_t)w0 * h->K : nullptr,
+                       d_bins ? d_bins + (size_t)w0 * h->n : nullptr, d_P64 ? d_P64 + (size_t)w0 * h->K : nullptr,
+                       d_R ? d_R + (size_t)w0 * h->m * h->m * 2 : nullptr, d_ev ? d_ev + (size_t)w0 * h->m : nullptr, st);
+        if (rc) return rc;
+    }
+    CU(h, cudaEventRecord(h->done[0], st));
+    h->ws_busy = true;
+    return MUSIC_B200_OK;
+}
+
+void free_host_staging(music_b200 *h)
+{
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->d_in[i]); cudaFree(h->d_ang[i]); cudaFree(h->d_lvl[i]); cudaFree(h->d_spec[i]); cudaFree(h->d_bins[i]);
+        h->d_in[i] = h->d_ang[i] = h->d_lvl[i] = h->d_spec[i] = nullptr;
+        h->d_bins[i] = nullptr;
+    }
+    h->host_chunk = 0;
+    h->host_spec_alloc = false;
+}
+
+int ensure_host_staging(music_b200 *h, uint32_t chunk, bool spec)
+{
+    if (chunk <= h->host_chunk && (!spec || h->host_spec_alloc)) return MUSIC_B200_OK;
+    const uint32_t cap = std::max(chunk, h->host_chunk);
+    free_host_staging(h);
+    for (int i = 0; i < 2; ++i) {
+        CU(h, cudaMalloc(&h->d_in[i], (size_t)cap * h->nsamples * 2 * sizeof(float)));
+        CU(h, cudaMalloc(&h->d_ang[i], (size_t)cap * h->n * sizeof(float)));
+        CU(h, cudaMalloc(&h->d_lvl[i], (size_t)cap * h->n * sizeof(float)));
+        CU(h, cudaMalloc(&h->d_bins[i], (size_t)cap * h->n * sizeof(int32_t)));
+        if (spec) CU(h, cudaMalloc(&h->d_spec[i], (size_t)cap * h->K * sizeof(float)));
+    }
+    h->host_chunk = cap;
+    h->host_spec_alloc = spec;
+    return MUSIC_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int music_b200_version(void) { return 1; }
+
+const char *music_b200_last_error(const music_b200 *h)
+{
+    if (h) return h->error.c_str();
+    std::lock_guard<std::mutex> g(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+uint64_t music_b200_launch_count(const music_b200 *h) { return h ? h->launches.load() : 0; }
+
+int music_b200_set_stage_timing(music_b200 *h, int enable)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    std::lock_guard<std::mutex> g(h->mutex);
+    h->timing = enable != 0;
+    h->tev_used = 0;
+    return MUSIC_B200_OK;
+}
+
+int music_b200_get_stage_times(music_b200 *h, double *ms4, uint64_t *chunks)
+{
+    if (!h || !ms4) return MUSIC_B200_EINVAL;
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    for (int i = 0; i < 4; ++i) ms4[i] = 0.0;
+    const size_t nch = h->tev_used / 5;
+    for (size_t c = 0; c < nch; ++c) {
+        cudaEvent_t *e = h->tev.data() + 5 * c;
+        CU(h, cudaEventSynchronize(e[4]));
+        for (int i = 0; i < 4; ++i) {
+            float ms = 0.f;
+            CU(h, cudaEventElapsedTime(&ms, e[i], e[i + 1]));
+            ms4[i] += ms;
+        }
+    }
+    if (chunks) *chunks = nch;
+    h->tev_used = 0;
+    return MUSIC_B200_OK;
+}
+
+int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsamples, uint32_t resolution,
+                      const float *table_c64, int device)
+{
+    if (!out) return fail(nullptr, MUSIC_B200_EINVAL, "out must not be NULL");
+    *out = nullptr;
+    // reference asserts, lib/baz_music_doa.cc:45-50 (+ n >= 1, n < m, see header)
+    if (m == 0 || m > MUSIC_B200_MAX_M) return fail(nullptr, MUSIC_B200_EINVAL, "m must be in 1..%d (got %u)", MUSIC_B200_MAX_M, m);
+    if (n == 0 || n >= m) return fail(nullptr, MUSIC_B200_EINVAL, "need 1 <= n < m (got n=%u, m=%u)", n, m);
+    if (nsamples == 0 || nsamples % m != 0) return fail(nullptr, MUSIC_B200_EINVAL, "nsamples must be a positive multiple of m (got %u)", nsamples);
+    if (resolution == 0) return fail(nullptr, MUSIC_B200_EINVAL, "resolution must be > 0");
+    if (!table_c64) return fail(nullptr, MUSIC_B200_EINVAL, "array response table must not be NULL");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MUSIC_B200_ENODEVICE, "no CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, MUSIC_B200_ENODEVICE, "device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, MUSIC_B200_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MUSIC_B200_ENODEVICE, "device %d is sm_%d%d; this build targets sm_100a only", device, prop.major, prop.minor);
+
+    music_b200 *h = new (std::nothrow) music_b200();
+    if (!h) return fail(nullptr, MUSIC_B200_ENOMEM, "out of host memory");
+    h->m = m; h->n = n; h->nsamples = nsamples; h->K = resolution; h->N = nsamples / m;
+    h->device = device; h->sm_count = prop.multiProcessorCount;
+
+    int rc = MUSIC_B200_OK;
+    auto init = [&]() -> int {
+        CU(h, cudaSetDevice(device));
+        for (int i = 0; i < 2; ++i) {
+            CU(h, cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+            CU(h, cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming));
+            CU(h, cudaMalloc(&h->table[i].c64, (size_t)resolution * m * 2 * sizeof(float)));
+            CU(h, cudaMalloc(&h->table[i].soa, soa_doubles(resolution, m) * sizeof(double)));
+        }
+        // scan kernels with M = 16 need 32 KiB dynamic smem (< 48 KiB default), nothing to opt in.
+        return upload_table(h, 0, table_c64, h->streams[0]);
+    };
+    rc = init();
+    if (rc != MUSIC_B200_OK) {
+        fail(nullptr, rc, "%s", h->error.c_str());
+        music_b200_destroy(h);
+        return rc;
+    }
+    h->cur_table = 0;
+    *out = h;
+    return MUSIC_B200_OK;
+}
+
+int music_b200_set_table(music_b200 *h, const float *table_c64)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (!table_c64) return fail(h, MUSIC_B200_EINVAL, "array response table must not be NULL");
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    // Work enqueued by earlier process_device() calls may still be reading the current slot on
+    // a caller stream; fill the other slot and flip.  (The slot being overwritten was retired
+    // two set_table() calls ago; synchronise the device once to be safe - retunes are rare.)
+    CU(h, cudaDeviceSynchronize());
+    const int slot = h->cur_table ^ 1;
+    int rc = upload_table(h, slot, table_c64, h->streams[0]);
+    if (rc) return rc;
+    h->cur_table = slot;
+    return MUSIC_B200_OK;
+}
+
+int music_b200_process_device_ex(music_b200 *h, const float *d_in_c64, uint32_t nwindows, float *d_angles,
+                                 float *d_levels, float *d_spectrum, int32_t *d_bins, double *d_P64, double *d_R,
+                                 double *d_eigvals, void *stream)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    return process_device_locked(h, d_in_c64, nwindows, d_angles, d_levels, d_spectrum, d_bins, d_P64, d_R, d_eigvals,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int music_b200_process_device(music_b200 *h, const float *d_in_c64, uint32_t nwindows, float *d_angles,
+                              float *d_levels, float *d_spectrum, int32_t *d_bins, void *stream)
+{
+    return music_b200_process_device_ex(h, d_in_c64, nwindows, d_angles, d_levels, d_spectrum, d_bins, nullptr, nullptr,
+                                        nullptr, stream);
+}
+
+int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindows, float *angles, float *levels,
+                            float *spectrum, int32_t *bins)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (nwindows == 0) return MUSIC_B200_OK;
+    if (!in_c64 || !angles) return fail(h, MUSIC_B200_EINVAL, "in_c64 and angles must not be NULL");
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    // chunk: ~32 MiB of input per copy, so that H2D of chunk i+1 overlaps compute of chunk i
+    const size_t win_bytes = (size_t)h->nsamples * 2 * sizeof(float);
+    uint32_t chunk = (uint32_t)std::max<size_t>(SCAN_B, ((size_t)32 << 20) / win_bytes);
+    chunk = std::min(chunk, (nwindows + 1) / 2 > SCAN_B ? (nwindows + 1) / 2 : nwindows);
+    chunk = std::max<uint32_t>(1, chunk);
+    int rc = ensure_host_staging(h, chunk, spectrum != nullptr);
+    if (rc) return rc;
+    // the two stream slots share the fp64 workspace, so kernels of slot i+1 must follow slot i:
+    // chain them with events; copies still overlap.
+    const bool internal_p64 = (h->n != 1);
+    rc = ensure_workspace(h, (chunk + SCAN_B - 1) / SCAN_B * SCAN_B, internal_p64);
+    if (rc) return rc;
+    int it = 0;
+    cudaEvent_t compute_done[2];
+    for (int i = 0; i < 2; ++i) CU(h, cudaEventCreateWithFlags(&compute_done[i], cudaEventDisableTiming));
+    rc = MUSIC_B200_OK;
+    for (uint32_t w0 = 0; w0 < nwindows && rc == MUSIC_B200_OK; w0 += chunk, ++it) {
+        const int s = it & 1;
+        const uint32_t W = std::min(chunk, nwindows - w0);
+        cudaStream_t st = h->streams[s];
+        if (it >= 2) CU(h, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
+        CU(h, cudaMemcpyAsync(h->d_in[s], in_c64 + (size_t)w0 * h->nsamples * 2, (size_t)W * win_bytes, cudaMemcpyHostToDevice, st));
+        if (it >= 1) CU(h, cudaStreamWaitEvent(st, compute_done[s ^ 1], 0));  // workspace hand-over
+        rc = run_chunk(h, h->d_in[s], W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
+                       nullptr, nullptr, nullptr, st);
+        if (rc) break;
+        CU(h, cudaEventRecord(compute_done[s], st));
+        CU(h, cudaMemcpyAsync(angles + (size_t)w0 * h->n, h->d_ang[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (levels) CU(h, cudaMemcpyAsync(levels + (size_t)w0 * h->n, h->d_lvl[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (bins) CU(h, cudaMemcpyAsync(bins + (size_t)w0 * h->n, h->d_bins[s], (size_t)W * h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (spectrum) CU(h, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
+    cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(compute_done[i]);
+    if (rc) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess)
+        return fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    return MUSIC_B200_OK;
+}
+
+void music_b200_destroy(music_b200 *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_host_staging(h);
+    cudaFree(h->d_R); cudaFree(h->d_evals); cudaFree(h->d_Vt); cudaFree(h->d_P64);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->table[i].c64); cudaFree(h->table[i].soa);
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+        if (h->done[i]) cudaEventDestroy(h->done[i]);
+    }
+    for (cudaEvent_t e : h->tev) cudaEventDestroy(e);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,547 @@
+// music_kernels.cuh - sm_100a kernels for the MUSIC DOA hot path (v1: three-stage pipeline).
+//
+// Stage map (reference = /root/reference/lib/baz_music_doa.cc):
+//   K1 cov_tile_kernel / cov_generic_kernel  <- :74-85  widen c64->f64, R = x x^H / N
+//   K2 eig_kernel                            <- :88-93  Hermitian eig, ascending, noise/signal split
+//   K3 scan_kernel (+ topn_kernel)           <- :103-155 pseudospectrum, top-n, float casts
+//   prep_table_kernel                        <- :110-112 (table widening, hoisted out of the loop)
+//
+// All arithmetic is fp64 (fp32 inputs are widened exactly; fp32 x fp32 products are exact in
+// fp64), because P(theta) = 1/||G^H a||^2 is ill-conditioned at the peak.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace music {
+
+constexpr int MAXM = 16;
+constexpr int TILE = 256;        // angles per steering-table tile == scan CTA size
+constexpr int SCAN_B = 8;        // windows per scan CTA
+constexpr double COMPLEMENT_GUARD = 0.0078125;  // 2^-7: below this fraction of ||a||^2 use the direct form
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: covariance, one warp per (window, 4x4 antenna tile).  Lanes stride over snapshots with
+// 128-bit coalesced loads (a snapshot's 4-antenna group is one 32-byte sector), accumulate the
+// tile in fp64 registers, then a warp-shuffle reduction.  R is written as full M x M complex
+// (row-major, interleaved re/im), lower triangle by conjugate symmetry.
+//   DIAG tile (I == I): Hermitian half only - 4 real diagonals + 6 complex = 16 accumulators,
+//                        32 DFMA per snapshot (2*M^2 for M = 4).
+//   OFF  tile (I <  J): full 4x4 complex block = 32 accumulators, 64 DFMA per snapshot.
+// ------------------------------------------------------------------------------------------
+template <bool OFF>
+__global__ void __launch_bounds__(256) cov_tile_kernel(const float *__restrict__ in, double *__restrict__ R,
+                                                       int W, int N, int M)
+{
+    const int T = M >> 2;                                   // tiles per dimension
+    const int tiles = OFF ? (T * (T - 1)) / 2 : T;          // tiles of this kind per window
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (item >= (long long)W * tiles) return;
+    const int w = (int)(item / tiles);
+    int t = (int)(item % tiles);
+    int I, J;
+    if (OFF) {  // enumerate I < J
+        I = 0;
+        while (t >= T - 1 - I) { t -= T - 1 - I; ++I; }
+        J = I + 1 + t;
+    } else {
+        I = J = t;
+    }
+    const float4 *base = reinterpret_cast<const float4 *>(in) + (size_t)w * N * (M >> 1);
+    const int rowq = M >> 1;  // float4 per snapshot
+
+    double acc[OFF ? 32 : 16];
+#pragma unroll
+    for (int i = 0; i < (OFF ? 32 : 16); ++i) acc[i] = 0.0;
+
+    constexpr int U = 4;  // snapshots in flight per lane
+    for (int c0 = lane; c0 < N; c0 += 32 * U) {
+        float4 xa[U][2], xb[U][2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + 32 * u;
+            if (c < N) {
+                const float4 *p = base + (size_t)c * rowq;
+                xa[u][0] = ldg_stream(p + 2 * I);
+                xa[u][1] = ldg_stream(p + 2 * I + 1);
+                if (OFF) {
+                    xb[u][0] = ldg_stream(p + 2 * J);
+                    xb[u][1] = ldg_stream(p + 2 * J + 1);
+                }
+            } else {
+                xa[u][0] = xa[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (OFF) xb[u][0] = xb[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double ar[4], ai[4];
+            ar[0] = xa[u][0].x; ai[0] = xa[u][0].y; ar[1] = xa[u][0].z; ai[1] = xa[u][0].w;
+            ar[2] = xa[u][1].x; ai[2] = xa[u][1].y; ar[3] = xa[u][1].z; ai[3] = xa[u][1].w;
+            if (OFF) {
+                double br[4], bi[4];
+                br[0] = xb[u][0].x; bi[0] = xb[u][0].y; br[1] = xb[u][0].z; bi[1] = xb[u][0].w;
+                br[2] = xb[u][1].x; bi[2] = xb[u][1].y; br[3] = xb[u][1].z; bi[3] = xb[u][1].w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // x_i * conj(y_j)
+                        acc[2 * (i * 4 + j)] = fma(ar[i], br[j], fma(ai[i], bi[j], acc[2 * (i * 4 + j)]));
+                        acc[2 * (i * 4 + j) + 1] = fma(ai[i], br[j], fma(-ar[i], bi[j], acc[2 * (i * 4 + j) + 1]));
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i] = fma(ar[i], ar[i], fma(ai[i], ai[i], acc[i]));
+                int e = 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = i + 1; j < 4; ++j) {
+                        acc[e] = fma(ar[i], ar[j], fma(ai[i], ai[j], acc[e]));
+                        acc[e + 1] = fma(ai[i], ar[j], fma(-ar[i], ai[j], acc[e + 1]));
+                        e += 2;
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < (OFF ? 32 : 16); ++i) acc[i] = warp_sum(acc[i]);
+
+    if (lane == 0) {
+        const double dn = (double)N;
+        double *Rw = R + (size_t)w * M * M * 2;
+        if (OFF) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double re = acc[2 * (i * 4 + j)] / dn, im = acc[2 * (i * 4 + j) + 1] / dn;
+                    const int r = 4 * I + i, c = 4 * J + j;
+                    Rw[2 * (r * M + c)] = re;  Rw[2 * (r * M + c) + 1] = im;
+                    Rw[2 * (c * M + r)] = re;  Rw[2 * (c * M + r) + 1] = -im;
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 4 * I + i;
+                Rw[2 * (r * M + r)] = acc[i] / dn;
+                Rw[2 * (r * M + r) + 1] = 0.0;
+            }
+            int e = 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = i + 1; j < 4; ++j) {
+                    const double re = acc[e] / dn, im = acc[e + 1] / dn;
+                    const int r = 4 * I + i, c = 4 * I + j;
+                    Rw[2 * (r * M + c)] = re;  Rw[2 * (r * M + c) + 1] = im;
+                    Rw[2 * (c * M + r)] = re;  Rw[2 * (c * M + r) + 1] = -im;
+                    e += 2;
+                }
+        }
+    }
+}
+
+// Generic-M covariance (any 2 <= M <= MAXM, used when M % 4 != 0): one CTA per window, thread
+// (entry e, slice s) accumulates R_ij over snapshots c = s, s+S, ...; slices summed in smem.
+__global__ void __launch_bounds__(256) cov_generic_kernel(const float *__restrict__ in, double *__restrict__ R,
+                                                          int W, int N, int M)
+{
+    extern __shared__ double sm[];  // [S][E][2]
+    const int w = blockIdx.x;
+    const int E = M * (M + 1) / 2;
+    const int S = blockDim.x / E;
+    const int e = threadIdx.x % E, s = threadIdx.x / E;
+    int i = 0, rem = e;
+    while (rem >= M - i) { rem -= M - i; ++i; }
+    const int j = i + rem;
+    const float2 *x = reinterpret_cast<const float2 *>(in) + (size_t)w * N * M;
+    double re = 0.0, im = 0.0;
+    if (s < S) {
+        for (int c = s; c < N; c += S) {
+            const float2 a = x[(size_t)c * M + i], b = x[(size_t)c * M + j];
+            const double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+            re = fma(ar, br, fma(ai, bi, re));
+            im = fma(ai, br, fma(-ar, bi, im));
+        }
+        sm[2 * (s * E + e)] = re;
+        sm[2 * (s * E + e) + 1] = im;
+    }
+    __syncthreads();
+    if (threadIdx.x < E) {
+        re = 0.0; im = 0.0;
+        for (int q = 0; q < S; ++q) { re += sm[2 * (q * E + e)]; im += sm[2 * (q * E + e) + 1]; }
+        re /= (double)N; im /= (double)N;
+        double *Rw = R + (size_t)w * M * M * 2;
+        if (i == j) im = 0.0;
+        Rw[2 * (i * M + j)] = re;  Rw[2 * (i * M + j) + 1] = im;
+        Rw[2 * (j * M + i)] = re;  Rw[2 * (j * M + i) + 1] = -im;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: Hermitian eigendecomposition, cyclic two-sided complex Jacobi, one thread per window
+// (SIMT over windows).  MT > 0: compile-time M (register arrays); MT == 0: runtime M <= MAXM.
+// Output Vt[w][j][i] = component i of eigenvector j, eigenvalues ascending (stable on ties),
+// so vectors 0..M-n-1 span the noise subspace G (:93) and M-n..M-1 the signal subspace.
+// ------------------------------------------------------------------------------------------
+template <int MA>
+__device__ __forceinline__ void jacobi_rotate(double (&Ar)[MA][MA], double (&Ai)[MA][MA], double (&Vr)[MA][MA],
+                                              double (&Vi)[MA][MA], const int p, const int q, const int M)
+{
+    const double gr = Ar[p][q], gi = Ai[p][q];
+    const double g = sqrt(gr * gr + gi * gi);
+    if (g == 0.0) return;
+    const double app = Ar[p][p], aqq = Ar[q][q];
+    const double er = gr / g, ei = gi / g;
+    const double theta = (aqq - app) / (2.0 * g);
+    double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));
+    if (theta < 0.0) t = -t;
+    const double c = 1.0 / sqrt(t * t + 1.0);
+    const double s = t * c;
+    const double swr = s * er, swi = s * ei;  // s * e,  e = a_pq / |a_pq|
+#pragma unroll
+    for (int k = 0; k < MA; ++k) {
+        if (k >= M) break;
+        if (k == p || k == q) continue;
+        const double kpr = Ar[k][p], kpi = Ai[k][p], kqr = Ar[k][q], kqi = Ai[k][q];
+        const double npr = c * kpr - (swr * kqr + swi * kqi);  // a_kp' = c a_kp - conj(s e) a_kq
+        const double npi = c * kpi - (swr * kqi - swi * kqr);
+        const double nqr = c * kqr + (swr * kpr - swi * kpi);  // a_kq' = (s e) a_kp + c a_kq
+        const double nqi = c * kqi + (swr * kpi + swi * kpr);
+        Ar[k][p] = npr; Ai[k][p] = npi; Ar[k][q] = nqr; Ai[k][q] = nqi;
+        Ar[p][k] = npr; Ai[p][k] = -npi; Ar[q][k] = nqr; Ai[q][k] = -nqi;
+    }
+    Ar[p][p] = app - t * g; Ai[p][p] = 0.0;
+    Ar[q][q] = aqq + t * g; Ai[q][q] = 0.0;
+    Ar[p][q] = 0.0; Ai[p][q] = 0.0; Ar[q][p] = 0.0; Ai[q][p] = 0.0;
+#pragma unroll
+    for (int k = 0; k < MA; ++k) {
+        if (k >= M) break;
+        const double kpr = Vr[k][p], kpi = Vi[k][p], kqr = Vr[k][q], kqi = Vi[k][q];
+        Vr[k][p] = c * kpr - (swr * kqr + swi * kqi);
+        Vi[k][p] = c * kpi - (swr * kqi - swi * kqr);
+        Vr[k][q] = c * kqr + (swr * kpr - swi * kpi);
+        Vi[k][q] = c * kqi + (swr * kpi + swi * kpr);
+    }
+}
+
+// MA = array extent; STATIC: M == MA at compile time, everything unrolled into registers
+// (M = 4); otherwise runtime M <= MA with the matrices in local memory.
+template <int MA, bool STATIC>
+__global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, double *__restrict__ evals,
+                                                  double *__restrict__ Vt, int Mrt, int W)
+{
+    const int M = STATIC ? MA : Mrt;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double Ar[MA][MA], Ai[MA][MA], Vr[MA][MA], Vi[MA][MA];
+    const double *Rw = R + (size_t)w * M * M * 2;
+    if (STATIC) {
+#pragma unroll
+        for (int i = 0; i < MA; ++i)
+#pragma unroll
+            for (int j = 0; j < MA; ++j) {
+                Ar[i][j] = Rw[2 * (i * MA + j)];
+                Ai[i][j] = Rw[2 * (i * MA + j) + 1];
+                Vr[i][j] = (i == j) ? 1.0 : 0.0;
+                Vi[i][j] = 0.0;
+            }
+    } else {
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) {
+                Ar[i][j] = Rw[2 * (i * M + j)];
+                Ai[i][j] = Rw[2 * (i * M + j) + 1];
+                Vr[i][j] = (i == j) ? 1.0 : 0.0;
+                Vi[i][j] = 0.0;
+            }
+    }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, fro = 0.0;
+        if (STATIC) {
+#pragma unroll
+            for (int i = 0; i < MA; ++i)
+#pragma unroll
+                for (int j = 0; j < MA; ++j) {
+                    const double e2 = Ar[i][j] * Ar[i][j] + Ai[i][j] * Ai[i][j];
+                    fro += e2;
+                    if (i != j) off += e2;
+                }
+        } else {
+            for (int i = 0; i < M; ++i)
+                for (int j = 0; j < M; ++j) {
+                    const double e2 = Ar[i][j] * Ar[i][j] + Ai[i][j] * Ai[i][j];
+                    fro += e2;
+                    if (i != j) off += e2;
+                }
+        }
+        if (off <= 1e-32 * fro || off == 0.0) break;
+        if (STATIC) {
+#pragma unroll
+            for (int p = 0; p < MA - 1; ++p)
+#pragma unroll
+                for (int q = p + 1; q < MA; ++q) jacobi_rotate<MA>(Ar, Ai, Vr, Vi, p, q, MA);
+        } else {
+#pragma unroll 1
+            for (int p = 0; p < M - 1; ++p)
+#pragma unroll 1
+                for (int q = p + 1; q < M; ++q) jacobi_rotate<MA>(Ar, Ai, Vr, Vi, p, q, M);
+        }
+    }
+    // ascending, stable: destination slot of column j = #{l : w_l < w_j} + #{l < j : w_l == w_j}
+    double *ew = evals + (size_t)w * M;
+    double *vw = Vt + (size_t)w * M * M * 2;
+    if (STATIC) {
+#pragma unroll
+        for (int j = 0; j < MA; ++j) {
+            int rank = 0;
+#pragma unroll
+            for (int l = 0; l < MA; ++l) rank += (Ar[l][l] < Ar[j][j]) || (l < j && Ar[l][l] == Ar[j][j]);
+            ew[rank] = Ar[j][j];
+#pragma unroll
+            for (int i = 0; i < MA; ++i) {
+                vw[2 * (rank * MA + i)] = Vr[i][j];
+                vw[2 * (rank * MA + i) + 1] = Vi[i][j];
+            }
+        }
+    } else {
+        for (int j = 0; j < M; ++j) {
+            int rank = 0;
+            for (int l = 0; l < M; ++l) rank += (Ar[l][l] < Ar[j][j]) || (l < j && Ar[l][l] == Ar[j][j]);
+            ew[rank] = Ar[j][j];
+            for (int i = 0; i < M; ++i) {
+                vw[2 * (rank * M + i)] = Vr[i][j];
+                vw[2 * (rank * M + i) + 1] = Vi[i][j];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Steering table preparation (once per set_table): c64 [K][M] -> fp64 SoA tiles
+//   soa[tile][comp][TILE],  comp = 2i (Re a_i), 2i+1 (Im a_i), 2M (||a||^2); zero padded.
+// Hoists the per-step c64 -> c128 widening of the reference (:110-112) out of the hot loop.
+// ------------------------------------------------------------------------------------------
+__global__ void prep_table_kernel(const float2 *__restrict__ tab, double *__restrict__ soa, int K, int M)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tile = k / TILE, j = k % TILE;
+    double *base = soa + (size_t)tile * (2 * M + 1) * TILE + j;
+    double na = 0.0;
+    for (int i = 0; i < M; ++i) {
+        double re = 0.0, im = 0.0;
+        if (k < K) { const float2 a = tab[(size_t)k * M + i]; re = a.x; im = a.y; }
+        base[(size_t)(2 * i) * TILE] = re;
+        base[(size_t)(2 * i + 1) * TILE] = im;
+        na = fma(re, re, fma(im, im, na));
+    }
+    base[(size_t)(2 * M) * TILE] = na;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: pseudospectrum scan.  One CTA per batch of SCAN_B windows; thread <-> angle bin within a
+// 256-bin table tile (its 2M+1 doubles live in registers), inner loop over the batch's windows
+// with the eigenvectors broadcast from shared memory.  Every bin is computed by the same
+// instruction sequence, so bit-equal table rows give bit-equal strengths (mirror ties).
+//
+//   d_k = ||G^H a_k||^2 is evaluated through the signal-subspace complement
+//         d = ||a||^2 - sum_s |e_s^H a|^2         (n < M-n: fewer flops)
+//   and recomputed in the direct noise-subspace form wherever d < 2^-7 ||a||^2 (near the
+//   peaks), so cancellation never costs more than ~2 digits.  P = 1.0 / d.
+//
+//   ARGMAX: n == 1 fused peak pick, ordered (P desc, bin asc), P > 0 strictly, NaN never.
+// ------------------------------------------------------------------------------------------
+struct PeakOut {
+    float *angles;   // [W][n]
+    float *levels;   // [W][n] or null
+    int32_t *bins;   // [W][n] or null
+};
+
+__device__ __forceinline__ bool peak_better(double Pa, int ka, double Pb, int kb)
+{
+    return (Pa > Pb) || (Pa == Pb && ka >= 0 && (kb < 0 || ka < kb));
+}
+
+template <int MT>
+__device__ __forceinline__ double strength_denominator(const double *ar, const double *ai, double na,
+                                                       const double *sv, int M, int n, bool use_sig)
+{
+    double d;
+    if (use_sig) {
+        double acc = 0.0;
+        for (int s = M - n; s < M; ++s) {
+            double cr = 0.0, ci = 0.0;
+#pragma unroll
+            for (int i = 0; i < (MT ? MT : MAXM); ++i) {
+                if (!MT && i >= M) break;
+                const double2 e = *reinterpret_cast<const double2 *>(sv + 2 * (s * M + i));
+                cr = fma(e.x, ar[i], fma(e.y, ai[i], cr));
+                ci = fma(e.x, ai[i], fma(-e.y, ar[i], ci));
+            }
+            acc = fma(cr, cr, fma(ci, ci, acc));
+        }
+        d = na - acc;
+        if (!(d < COMPLEMENT_GUARD * na)) return d;  // NaN falls through to the direct form (stays NaN)
+    }
+    double acc = 0.0;
+    for (int s = 0; s < M - n; ++s) {
+        double cr = 0.0, ci = 0.0;
+#pragma unroll
+        for (int i = 0; i < (MT ? MT : MAXM); ++i) {
+            if (!MT && i >= M) break;
+            const double2 e = *reinterpret_cast<const double2 *>(sv + 2 * (s * M + i));
+            cr = fma(e.x, ar[i], fma(e.y, ai[i], cr));
+            ci = fma(e.x, ai[i], fma(-e.y, ar[i], ci));
+        }
+        acc = fma(cr, cr, fma(ci, ci, acc));
+    }
+    d = acc;
+    return d;
+}
+
+template <int MT, bool ARGMAX, bool WRITE_P64, bool WRITE_SPEC>
+__global__ void __launch_bounds__(TILE) scan_kernel(const double *__restrict__ soa, const double *__restrict__ Vt,
+                                                    int Mrt, int n, int K, int W, PeakOut out,
+                                                    float *__restrict__ spectrum, double *__restrict__ P64)
+{
+    constexpr int MA = MT ? MT : MAXM;
+    const int M = MT ? MT : Mrt;
+    extern __shared__ __align__(16) double smem[];
+    double *sV = smem;  // [SCAN_B][M*M*2]
+    const int w0 = blockIdx.x * SCAN_B;
+    const int nb = min(SCAN_B, W - w0);
+    const int vsz = M * M * 2;
+    for (int i = threadIdx.x; i < nb * vsz; i += blockDim.x) sV[i] = Vt[(size_t)w0 * vsz + i];
+    __syncthreads();
+
+    const bool use_sig = (n < M - n);
+    double bestP[SCAN_B];
+    int bestk[SCAN_B];
+#pragma unroll
+    for (int b = 0; b < SCAN_B; ++b) { bestP[b] = 0.0; bestk[b] = -1; }
+
+    const int ntiles = (K + TILE - 1) / TILE;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int k = tile * TILE + threadIdx.x;
+        const double *tb = soa + (size_t)tile * (2 * M + 1) * TILE + threadIdx.x;
+        double ar[MA], ai[MA];
+#pragma unroll
+        for (int i = 0; i < MA; ++i) {
+            if (!MT && i >= M) break;
+            ar[i] = tb[(size_t)(2 * i) * TILE];
+            ai[i] = tb[(size_t)(2 * i + 1) * TILE];
+        }
+        const double na = tb[(size_t)(2 * M) * TILE];
+        if (k < K) {
+#pragma unroll
+            for (int b = 0; b < SCAN_B; ++b) {
+                if (b < nb) {
+                    const double d = strength_denominator<MT>(ar, ai, na, sV + b * vsz, M, n, use_sig);
+                    const double P = 1.0 / d;
+                    if (WRITE_SPEC) spectrum[(size_t)(w0 + b) * K + k] = (float)P;
+                    if (WRITE_P64) P64[(size_t)(w0 + b) * K + k] = P;
+                    if (ARGMAX) {
+                        if (P > bestP[b]) { bestP[b] = P; bestk[b] = k; }  // k ascending per thread: strict > keeps the lower bin
+                    }
+                }
+            }
+        }
+    }
+    if (ARGMAX) {
+        __shared__ double rP[SCAN_B][TILE / 32];
+        __shared__ int rk[SCAN_B][TILE / 32];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int b = 0; b < SCAN_B; ++b) {
+            double P = bestP[b];
+            int kk = bestk[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double Po = __shfl_xor_sync(0xffffffffu, P, o);
+                const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
+                if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
+            }
+            if (lane == 0) { rP[b][wid] = P; rk[b][wid] = kk; }
+        }
+        __syncthreads();
+        if (threadIdx.x < nb) {
+            const int b = threadIdx.x;
+            double P = rP[b][0];
+            int kk = rk[b][0];
+            for (int q = 1; q < TILE / 32; ++q)
+                if (peak_better(rP[b][q], rk[b][q], P, kk)) { P = rP[b][q]; kk = rk[b][q]; }
+            const size_t o = (size_t)(w0 + b);  // n == 1
+            if (kk >= 0) {
+                out.angles[o] = (float)((double)kk * 360.0 / (double)K);  // :134, :153
+                if (out.levels) out.levels[o] = (float)P;                 // :154
+            } else {
+                out.angles[o] = 0.f;                                      // (0,0) initial pair, :95
+                if (out.levels) out.levels[o] = 0.f;
+            }
+            if (out.bins) out.bins[o] = kk;
+        }
+    }
+}
+
+// Top-n for n >= 2 from the fp64 strengths: one warp per window, n rounds of a warp arg-max in
+// the reference's total order (P desc, bin asc; P > 0 strictly; NaN never) - equivalent to the
+// insertion loop at :129-141.
+__global__ void __launch_bounds__(256) topn_kernel(const double *__restrict__ P64, int n, int K, int W, PeakOut out)
+{
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= W) return;
+    const double *P = P64 + (size_t)w * K;
+    double prevP = 0.0;
+    int prevk = -1;
+    bool first = true;
+    for (int r = 0; r < n; ++r) {
+        double bP = 0.0;
+        int bk = -1;
+        if (first || prevk >= 0) {
+            for (int k = lane; k < K; k += 32) {
+                const double p = P[k];
+                const bool after = first || (p < prevP) || (p == prevP && k > prevk);
+                if (after && p > 0.0 && p > bP) { bP = p; bk = k; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double Po = __shfl_xor_sync(0xffffffffu, bP, o);
+                const int ko = __shfl_xor_sync(0xffffffffu, bk, o);
+                if (peak_better(Po, ko, bP, bk)) { bP = Po; bk = ko; }
+            }
+        }
+        if (lane == 0) {
+            const size_t o = (size_t)w * n + r;
+            if (bk >= 0) {
+                out.angles[o] = (float)((double)bk * 360.0 / (double)K);
+                if (out.levels) out.levels[o] = (float)bP;
+            } else {
+                out.angles[o] = 0.f;
+                if (out.levels) out.levels[o] = 0.f;
+            }
+            if (out.bins) out.bins[o] = bk;
+        }
+        first = false;
+        prevP = bP;
+        prevk = bk;
+    }
+}
+
+}  // namespace music

@@ -1,0 +1,140 @@
+"""Python mirror of the reference block ``baz.music_doa`` (SWIG name,
+/root/reference/swig/baz_swig.i:562-572; C++ class /root/reference/lib/baz_music_doa.h:38-60).
+
+Same constructor arguments, ``set_array_response`` and ``work`` contract:
+
+    blk = music_doa(m, n, nsamples, array_response, resolution)
+    produced = blk.work(noutput_items, [in_items], [angles, levels(, spectrum)])
+
+``array_response`` is the nested list ``[resolution][m]`` of complex the helper builds; it is
+rounded to complex64 exactly as SWIG does when filling ``std::vector<std::vector<gr_complex>>``.
+``work`` takes numpy arrays in the GNU Radio item layouts (input items of ``nsamples``
+complex64; output items of ``n`` / ``n`` / ``resolution`` float32) and, unlike the reference
+(which returns 1, lib/baz_music_doa.cc:160), consumes all ``noutput_items`` windows per call -
+legal for a gr::sync_block and the only way a GPU gets a batch; per-window results are the
+reference's.  All compute happens in the CUDA library behind include/music_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+import sys
+import threading
+
+import numpy as np
+
+from . import _capi
+
+_uid = [0]
+_uid_lock = threading.Lock()
+
+
+def _table_c64(array_response, resolution, m):
+    t = np.asarray(array_response, dtype=np.complex128)
+    if t.ndim != 2 or t.shape[0] != resolution or t.shape[1] != m:
+        # reference: assert(array_response.size() == resolution); assert(array_response[0].size() == m)
+        raise ValueError("array_response must be [resolution=%d][m=%d], got %s" % (resolution, m, t.shape))
+    return np.ascontiguousarray(t.astype(np.complex64))
+
+
+class music_doa(object):
+    def __init__(self, m, n, nsamples, array_response, resolution, device=0):
+        self._lib = _capi.load()
+        self._h = ctypes.c_void_p()
+        self.m, self.n, self.nsamples, self.resolution = int(m), int(n), int(nsamples), int(resolution)
+        if self.m <= 0 or self.resolution <= 0:
+            raise ValueError("m and resolution must be > 0")
+        table = _table_c64(array_response, self.resolution, self.m)
+        rc = self._lib.music_b200_create(ctypes.byref(self._h), self.m, self.n, self.nsamples, self.resolution,
+                                         table.ctypes.data, int(device))
+        if rc == _capi.EINVAL:
+            raise ValueError(self._lib.music_b200_last_error(None).decode())
+        _capi.check(rc)
+        with _uid_lock:
+            _uid[0] += 1
+            self._unique_id = _uid[0]
+        # banner, reference lib/baz_music_doa.cc:52
+        sys.stderr.write("[%s<%i>] MUSIC DOA: M: %d, N: %d, # samples: %d, angular resolution: %d\n"
+                         % (self.name(), self._unique_id, self.m, self.n, self.nsamples, self.resolution))
+
+    # -- gr::basic_block look-alikes used by the banner ---------------------------------
+    def name(self):
+        return "music_doa"
+
+    def unique_id(self):
+        return self._unique_id
+
+    def input_signature(self):
+        """(min, max, [item sizes]) - reference lib/baz_music_doa.cc:37"""
+        return (1, 1, [self.nsamples * 8])
+
+    def output_signature(self):
+        """reference lib/baz_music_doa.cc:38 (make3(1, 3, n*4, n*4, resolution*4))"""
+        return (1, 3, [self.n * 4, self.n * 4, self.resolution * 4])
+
+    # -- reference API ------------------------------------------------------------------
+    def set_array_response(self, array_response):
+        table = _table_c64(array_response, self.resolution, self.m)
+        sys.stderr.write("[%s<%i>] Updating array response\n" % (self.name(), self._unique_id))  # :65
+        _capi.check(self._lib.music_b200_set_table(self._h, table.ctypes.data), self._h)
+
+    def work(self, noutput_items, input_items, output_items):
+        """input_items[0]: complex64 (noutput_items, nsamples); output_items: 1..3 float32 arrays
+        (angles (., n), levels (., n), spectrum (., resolution)).  Returns items produced."""
+        W = int(noutput_items)
+        if W <= 0:
+            return 0
+        x = input_items[0]
+        if x.dtype != np.complex64 or not x.flags["C_CONTIGUOUS"] or x.size < W * self.nsamples:
+            raise ValueError("input_items[0] must be C-contiguous complex64 with >= noutput_items*nsamples elements")
+        outs = list(output_items)
+        if not 1 <= len(outs) <= 3:
+            raise ValueError("1 to 3 output ports")
+        sizes = [self.n, self.n, self.resolution]
+        for o, s in zip(outs, sizes):
+            if o.dtype != np.float32 or not o.flags["C_CONTIGUOUS"] or o.size < W * s:
+                raise ValueError("output buffers must be C-contiguous float32 of the port's item size")
+        ang = outs[0]
+        lvl = outs[1] if len(outs) > 1 else None
+        spec = outs[2] if len(outs) > 2 else None
+        self._last_bins = np.empty((W, self.n), np.int32)
+        rc = self._lib.music_b200_process_host(
+            self._h, x.ctypes.data, W, ang.ctypes.data, lvl.ctypes.data if lvl is not None else None,
+            spec.ctypes.data if spec is not None else None, self._last_bins.ctypes.data)
+        _capi.check(rc, self._h)
+        return W
+
+    # -- extras (not in the reference) ---------------------------------------------------
+    def last_bins(self):
+        """int32 (W, n) peak-bin indices of the last work() call (-1 = unfilled slot)."""
+        return self._last_bins
+
+    def process_device(self, d_in, nwindows, d_angles, d_levels=None, d_spectrum=None, d_bins=None,
+                       stream=None, d_P64=None, d_R=None, d_eigvals=None):
+        """Raw device-pointer entry (ints); buffers stay resident in HBM."""
+        rc = self._lib.music_b200_process_device_ex(
+            self._h, d_in, int(nwindows), d_angles, d_levels, d_spectrum, d_bins, d_P64, d_R, d_eigvals, stream)
+        _capi.check(rc, self._h)
+
+    def set_stage_timing(self, enable):
+        _capi.check(self._lib.music_b200_set_stage_timing(self._h, 1 if enable else 0), self._h)
+
+    def stage_times_ms(self):
+        """(ms[4] = cov, eig, scan, topn accumulated since the last call; chunks)"""
+        ms = (ctypes.c_double * 4)()
+        ch = ctypes.c_uint64(0)
+        _capi.check(self._lib.music_b200_get_stage_times(self._h, ms, ctypes.byref(ch)), self._h)
+        return list(ms), int(ch.value)
+
+    def launch_count(self):
+        return int(self._lib.music_b200_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.music_b200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

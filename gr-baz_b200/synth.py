@@ -97,10 +97,17 @@ def _window_keys(seed: int, w):
 _FRACS = np.array([0.1, 0.15, 0.2, 0.25, 0.3, 0.35, 0.4, 0.6, 0.65, 0.7, 0.75, 0.8, 0.85, 0.9])
 
 
-def window_params(cfg, seed: int, w0: int, W: int):
+def _windex(w0, W, indices):
+    if indices is not None:
+        return np.asarray(indices, dtype=np.int64)
+    return np.arange(w0, w0 + W, dtype=np.int64)
+
+
+def window_params(cfg, seed: int, w0: int = 0, W: int = 0, indices=None):
     """Host-side (numpy) per-window parameters: true source angles in degrees (W, S) and
-    the fp32 rotated-phasor table rot[w, ant, sym, comp] = (amp * a_s(phi) * j^sym)."""
-    w = np.arange(w0, w0 + W, dtype=np.int64)
+    the fp32 rotated-phasor table rot[w, ant, sym, comp] = (amp * a_s(phi) * j^sym).
+    Windows are w0..w0+W-1, or the explicit global window numbers in ``indices``."""
+    w = _windex(w0, W, indices)
     _, _, k_ang = _window_keys(seed, w)
     K = cfg["resolution"]
     h1 = _h32(k_ang)
@@ -130,12 +137,13 @@ def _noise_scale(cfg) -> np.float32:
     return np.float32(math.sqrt(sigma2 / 2.0) / ih_std)
 
 
-def gen_windows_numpy(cfg, seed: int, w0: int, W: int):
+def gen_windows_numpy(cfg, seed: int, w0: int = 0, W: int = 0, indices=None):
     """(W, nsamples) complex64, host reference generator."""
     M, N = cfg["m"], cfg["snapshots"]
-    _, rot32 = window_params(cfg, seed, w0, W)
+    w = _windex(w0, W, indices)
+    W = len(w)
+    _, rot32 = window_params(cfg, seed, indices=w)
     S = rot32.shape[1]
-    w = np.arange(w0, w0 + W, dtype=np.int64)
     k_noise, k_sym, _ = _window_keys(seed, w)
     idx = np.arange(N * M * 2, dtype=np.int64)
     hn = _h32((k_noise[:, None] + idx[None, :]) & M32)
@@ -154,12 +162,14 @@ def gen_windows_numpy(cfg, seed: int, w0: int, W: int):
     return np.ascontiguousarray(x.reshape(W, N * M * 2)).view(np.complex64)
 
 
-def gen_windows_torch(cfg, seed: int, w0: int, W: int, device, out=None, chunk: int = 64):
+def gen_windows_torch(cfg, seed: int, w0: int, W: int, device, out=None, chunk: int = 64, indices=None):
     """Same stream generated with torch ops on ``device``; returns float32 (W, nsamples*2)
     (interleaved re, im).  Bit-identical to gen_windows_numpy (tests/test_synth.py)."""
     import torch
 
     M, N = cfg["m"], cfg["snapshots"]
+    wall = _windex(w0, W, indices)
+    W = len(wall)
     if out is None:
         out = torch.empty((W, N * M * 2), dtype=torch.float32, device=device)
     scale = torch.tensor(float(_noise_scale(cfg)), dtype=torch.float32, device=device)
@@ -167,9 +177,9 @@ def gen_windows_torch(cfg, seed: int, w0: int, W: int, device, out=None, chunk: 
     cidx = torch.arange(N, dtype=torch.int64, device=device)
     for c0 in range(0, W, chunk):
         cw = min(chunk, W - c0)
-        _, rot32 = window_params(cfg, seed, w0 + c0, cw)
+        w = wall[c0 : c0 + cw]
+        _, rot32 = window_params(cfg, seed, indices=w)
         S = rot32.shape[1]
-        w = np.arange(w0 + c0, w0 + c0 + cw, dtype=np.int64)
         k_noise, k_sym, _ = _window_keys(seed, w)
         k_noise = torch.from_numpy(k_noise).to(device)
         k_sym = torch.from_numpy(k_sym).to(device)
@@ -191,9 +201,9 @@ def gen_windows_torch(cfg, seed: int, w0: int, W: int, device, out=None, chunk: 
     return out
 
 
-def true_bins(cfg, seed: int, w0: int, W: int):
+def true_bins(cfg, seed: int, w0: int = 0, W: int = 0, indices=None):
     """Nearest grid bin of each true source angle (diagnostic; the parity gate is the
     oracle's bins, not these)."""
-    ang, _ = window_params(cfg, seed, w0, W)
+    ang, _ = window_params(cfg, seed, w0, W, indices)
     K = cfg["resolution"]
     return np.rint(ang * K / 360.0).astype(np.int64) % K

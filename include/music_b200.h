@@ -1,0 +1,118 @@
+/*
+ * music_b200.h - C ABI of the B200-native (sm_100a) MUSIC direction-of-arrival hot path.
+ *
+ * This is the drop-in boundary for gr-baz's `baz_music_doa` block: everything that
+ * /root/reference/lib/baz_music_doa.cc does per window inside work() (lines 72-161) runs
+ * behind these entry points as hand-written CUDA; the GNU Radio block (lib/baz_music_doa.cc
+ * in this repo), the Python helper and the bench harness are the only callers.
+ *
+ * Plain C types only: pointers and sizes, no C++/torch types, no exceptions.  Every function
+ * returns 0 on success or a negative MUSIC_B200_E* code; the message is available from
+ * music_b200_last_error().  There is NO CPU fallback: create() fails if the device is not a
+ * compute-capability 10.x GPU.
+ *
+ * Data layouts (identical to the reference's GNU Radio item layouts):
+ *   input window : nsamples complex64 (re, im floats), antennas sample-interleaved,
+ *                  x(r, c) = in[c*m + r]            (reference lib/baz_music_doa.cc:37, :82-84)
+ *   array response table : [resolution][m] complex64  (reference lib/baz_music_doa.h:32-33,
+ *                  marshalled by swig/baz_swig.i:564)
+ *   angles / levels : n floats per window             (reference lib/baz_music_doa.cc:38, :146-155)
+ *   spectrum        : resolution floats per window    (reference lib/baz_music_doa.cc:38, :120-121)
+ *   bins            : n int32 per window - the integer peak-bin index k behind each angle
+ *                     (angle = (float)(k*360.0/resolution), :134); -1 where the reference
+ *                     would leave its (0, 0) initial pair in place (:95).
+ */
+#ifndef MUSIC_B200_H
+#define MUSIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUSIC_B200_OK 0
+#define MUSIC_B200_EINVAL (-1)   /* bad argument (same conditions as the reference's ctor asserts) */
+#define MUSIC_B200_ECUDA (-2)    /* CUDA runtime error */
+#define MUSIC_B200_ENODEVICE (-3) /* no sm_100-class device / device index out of range */
+#define MUSIC_B200_ENOMEM (-4)
+
+#define MUSIC_B200_MAX_M 16 /* antennas supported by this build */
+
+typedef struct music_b200 music_b200;
+
+/* ABI version of this header (bumped on any signature change). */
+int music_b200_version(void);
+
+/*
+ * Replaces baz_make_music_doa() + the constructor
+ * (/root/reference/lib/baz_music_doa.cc:29-53, lib/baz_music_doa.h:36-43).
+ * Argument checks are the reference's asserts (:45-50) made real, plus 1 <= n < m
+ * (m == n underflows eigvec.cols(0, m-n-1) at :93) and m <= MUSIC_B200_MAX_M.
+ * table_c64: [resolution][m] interleaved (re, im) floats, copied (the block owns its table,
+ * :42).  device: CUDA device ordinal.
+ */
+int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsamples,
+                      uint32_t resolution, const float *table_c64, int device);
+
+/*
+ * Replaces baz_music_doa::set_array_response() (/root/reference/lib/baz_music_doa.cc:60-70).
+ * Thread-safe against a concurrent process_*() call, like the reference's d_mutex (:67, :101):
+ * a call in flight finishes with the old table, later calls see the new one.
+ */
+int music_b200_set_table(music_b200 *h, const float *table_c64);
+
+/*
+ * Replaces the body of baz_music_doa::work() (/root/reference/lib/baz_music_doa.cc:72-161)
+ * for `nwindows` consecutive input items held in HOST memory (what the GNU Radio scheduler
+ * hands to work(): input_items[0], output_items[0..2]).  Host<->device copies are done
+ * inside (chunked, double-buffered).  levels / spectrum / bins may be NULL, mirroring
+ * output_items.size() (:97-99, :148-149); NULL skips that work.
+ */
+int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindows,
+                            float *angles, float *levels, float *spectrum, int32_t *bins);
+
+/*
+ * Same computation with all buffers already resident in device memory (the streaming /
+ * benchmark path, and the entry a device-resident upstream block would call).  Enqueued on
+ * `stream` (a cudaStream_t, NULL = legacy default stream); does not synchronise.
+ * d_in must be 16-byte aligned.
+ */
+int music_b200_process_device(music_b200 *h, const float *d_in_c64, uint32_t nwindows,
+                              float *d_angles, float *d_levels, float *d_spectrum,
+                              int32_t *d_bins, void *stream);
+
+/*
+ * process_device plus optional fp64 internals for stage-by-stage parity tests against the
+ * oracle (any of them may be NULL):
+ *   d_P64     [nwindows][resolution]  strength = 1/||G^H a||^2 before the float cast (:114-119)
+ *   d_R       [nwindows][m][m][2]     covariance R = x x^H / N (:85)
+ *   d_eigvals [nwindows][m]           ascending eigenvalues (:88-90)
+ */
+int music_b200_process_device_ex(music_b200 *h, const float *d_in_c64, uint32_t nwindows,
+                                 float *d_angles, float *d_levels, float *d_spectrum,
+                                 int32_t *d_bins, double *d_P64, double *d_R,
+                                 double *d_eigvals, void *stream);
+
+/* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
+uint64_t music_b200_launch_count(const music_b200 *h);
+
+/*
+ * Optional per-stage device timing for the benchmark's roofline leg.  While enabled, every
+ * internal chunk records CUDA events on the launch stream around K1 (covariance), K2
+ * (eigendecomposition), K3 (scan) and the top-n kernel.  get_stage_times() synchronises on
+ * them, returns the accumulated milliseconds since the last call in ms4[0..3] and the number
+ * of chunks in *chunks (may be NULL), then resets the accumulation.
+ */
+int music_b200_set_stage_timing(music_b200 *h, int enable);
+int music_b200_get_stage_times(music_b200 *h, double *ms4, uint64_t *chunks);
+
+/* Last error text for this handle; h == NULL returns the last create() failure. */
+const char *music_b200_last_error(const music_b200 *h);
+
+void music_b200_destroy(music_b200 *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSIC_B200_H */

@@ -1,0 +1,249 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+the oracle on the same seeded inputs, against the committed golden fixtures, and - at
+BASELINE.json's full sizes - through size-independent properties.
+
+Gates (BASELINE.json north_star): peak-bin indices bit-exact; P(theta) <= 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gr_baz_b200 import synth
+from gr_baz_b200.music_doa import music_doa
+from gr_baz_b200.music_doa_helper import music_doa_helper
+from oracle import c_oracle as co
+from oracle import music_oracle as mo
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+P_RTOL = 1e-5  # the north_star tolerance on P(theta)
+
+
+def run_block(cfg, table, x, spectrum=True, device_path=False, want_internals=False):
+    """x: (W, nsamples) complex64 host array.  Returns dict of host arrays."""
+    W = x.shape[0]
+    blk = music_doa(cfg["m"], cfg["n"], cfg["nsamples"], table.tolist(), cfg["resolution"])
+    out = {}
+    if not device_path:
+        ang = np.full((W, cfg["n"]), -7, np.float32)
+        lvl = np.full((W, cfg["n"]), -7, np.float32)
+        outs = [ang, lvl]
+        if spectrum:
+            spec = np.zeros((W, cfg["resolution"]), np.float32)
+            outs.append(spec)
+            out["spectrum"] = spec
+        assert blk.work(W, [x], outs) == W
+        out.update(angles=ang, levels=lvl, bins=blk.last_bins().copy())
+    else:
+        dev = torch.device("cuda:0")
+        d_in = torch.from_numpy(x.view(np.float32)).to(dev)
+        d_ang = torch.empty((W, cfg["n"]), dtype=torch.float32, device=dev)
+        d_lvl = torch.empty_like(d_ang)
+        d_bins = torch.empty((W, cfg["n"]), dtype=torch.int32, device=dev)
+        d_spec = torch.empty((W, cfg["resolution"]), dtype=torch.float32, device=dev) if spectrum else None
+        d_P = torch.empty((W, cfg["resolution"]), dtype=torch.float64, device=dev) if want_internals else None
+        d_R = torch.empty((W, cfg["m"], cfg["m"], 2), dtype=torch.float64, device=dev) if want_internals else None
+        d_ev = torch.empty((W, cfg["m"]), dtype=torch.float64, device=dev) if want_internals else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        blk.process_device(ptr(d_in), W, ptr(d_ang), ptr(d_lvl), ptr(d_spec), ptr(d_bins),
+                           stream=torch.cuda.current_stream().cuda_stream, d_P64=ptr(d_P), d_R=ptr(d_R), d_eigvals=ptr(d_ev))
+        torch.cuda.synchronize()
+        out.update(angles=d_ang.cpu().numpy(), levels=d_lvl.cpu().numpy(), bins=d_bins.cpu().numpy())
+        if spectrum:
+            out["spectrum"] = d_spec.cpu().numpy()
+        if want_internals:
+            R = d_R.cpu().numpy()
+            out.update(P=d_P.cpu().numpy(), R=R[..., 0] + 1j * R[..., 1], eigvals=d_ev.cpu().numpy())
+    out["launches"] = blk.launch_count()
+    blk.close()
+    return out
+
+
+def assert_parity(got, ref, n, check_spectrum=True):
+    assert np.array_equal(got["bins"], ref["bins"]), np.argwhere(got["bins"] != ref["bins"])[:5]
+    assert np.array_equal(got["angles"], ref["angles"])
+    valid = ref["bins"] >= 0
+    assert helpers.rel_err(got["levels"][valid], ref["levels"][valid]) <= P_RTOL
+    if check_spectrum and "spectrum" in got:
+        assert helpers.rel_err(got["spectrum"], ref["P"]) <= P_RTOL
+    if "P" in got:
+        assert helpers.rel_err(got["P"], ref["P"]) <= P_RTOL
+
+
+@pytest.mark.parametrize("path", helpers.golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_golden_fixtures(path):
+    cfg, seed, table, wins, _ = helpers.load_golden(path)
+    x = np.stack([g["in"] for g in wins])
+    ref = {k: np.stack([g[k] for g in wins]) for k in ("bins", "angles", "levels", "P", "R", "eigvals")}
+    for device_path in (False, True):
+        got = run_block(cfg, table, x, spectrum=True, device_path=device_path, want_internals=device_path)
+        assert_parity(got, ref, cfg["n"])
+        assert got["launches"] > 0
+        if device_path:
+            scale = np.max(np.abs(ref["R"]))
+            assert np.max(np.abs(got["R"] - ref["R"])) <= 1e-12 * scale
+            assert np.max(np.abs(got["eigvals"] - ref["eigvals"])) <= 1e-11 * scale
+            assert helpers.rel_err(got["P"], ref["P"]) <= 1e-8  # far inside the 1e-5 gate
+
+
+SEEDED = [
+    # base cfg, overrides, windows
+    (1, {}, 67),
+    (1, dict(snr_db=0.0), 33),
+    (1, dict(snr_db=40.0, geometry="ula_y"), 16),
+    (1, dict(n=2, geometry="uca"), 16),
+    (1, dict(n=3, geometry="uca"), 9),
+    (1, dict(snapshots=128), 40),       # GRC default operating point
+    (1, dict(snapshots=7), 8),          # fewer snapshots than lanes
+    (1, dict(resolution=100), 8),       # K < one table tile
+    (1, dict(resolution=777), 8),       # K not a multiple of the tile
+    (2, {}, 24),
+    (2, dict(snr_db=40.0), 8),
+    (4, {}, 12),
+    (4, dict(n=3), 5),
+    (4, dict(n=5), 5),                  # n > M - n: direct noise-subspace form only
+    (5, {}, 6),
+    (5, dict(n=1, snapshots=512), 6),
+    (1, dict(m=3, geometry="uca", n=1), 8),      # generic-M kernels
+    (1, dict(m=5, geometry="uca", n=2), 8),
+    (1, dict(m=6, geometry="uca", n=2, snapshots=200), 8),
+    (1, dict(m=12, geometry="uca", n=2, snapshots=256), 6),
+    (1, dict(m=2, geometry="ula_y", n=1, snapshots=256), 8),
+]
+
+
+@pytest.mark.parametrize("base,over,W", SEEDED, ids=lambda v: str(v).replace(" ", ""))
+def test_seeded_batches_match_oracle(base, over, W):
+    cfg = synth.config(base, **over)
+    table = helpers.table_for(cfg)
+    seed = synth.BASE_SEED + 100 + base
+    x = synth.gen_windows_numpy(cfg, seed, 0, W)
+    ref = co.work_batch(x, cfg["m"], cfg["n"], table, want_spectrum=False)
+    got = run_block(cfg, table, x, spectrum=True, device_path=True, want_internals=True)
+    assert_parity(got, ref, cfg["n"])
+    got_h = run_block(cfg, table, x, spectrum=False, device_path=False)
+    assert_parity(got_h, ref, cfg["n"])
+    # numpy/LAPACK oracle on a couple of windows as well
+    for w in (0, W - 1):
+        r = mo.work(x[w], cfg["m"], cfg["n"], table)
+        assert np.array_equal(got["bins"][w], r["bins"])
+        assert helpers.rel_err(got["P"][w], r["P"]) <= P_RTOL
+
+
+def test_edge_windows():
+    cfg = synth.config(1)
+    table = helpers.table_for(cfg)
+    x = synth.gen_windows_numpy(cfg, 5, 0, 6)
+    x[1] = 0  # all-zero window: R = 0, eigenvectors = identity
+    x[3] *= np.float32(2.0 ** -60)  # tiny but normal
+    x[4] *= np.float32(2.0 ** 40)   # large
+    ref = co.work_batch(x, 4, 1, table)
+    got = run_block(cfg, table, x, spectrum=True, device_path=True, want_internals=True)
+    assert_parity(got, ref, 1)
+    # NaN window: nothing is ever inserted (strict '>' is false for NaN): (0, 0), bin -1
+    x[2, 17] = np.nan
+    got = run_block(cfg, table, x, spectrum=False, device_path=False)
+    assert got["bins"][2, 0] == -1 and got["angles"][2, 0] == 0.0 and got["levels"][2, 0] == 0.0
+    assert np.array_equal(got["bins"][[0, 1, 3, 4, 5]], ref["bins"][[0, 1, 3, 4, 5]])
+    # single window, single snapshot
+    c1 = synth.config(1, snapshots=1)
+    x1 = synth.gen_windows_numpy(c1, 9, 0, 1)
+    assert_parity(run_block(c1, table, x1, device_path=True, want_internals=True), co.work_batch(x1, 4, 1, table), 1)
+
+
+def test_mirror_ties_resolve_to_lower_bin():
+    # x-axis ULA: P[k] == P[K-k] exactly; every bin must be computed by the same instruction
+    # sequence so the tie is exact on the GPU too, and the lower bin must win.
+    cfg = synth.config(1)
+    table = helpers.table_for(cfg)
+    x = synth.gen_windows_numpy(cfg, 4321, 0, 32)
+    got = run_block(cfg, table, x, spectrum=True, device_path=True, want_internals=True)
+    K = cfg["resolution"]
+    k = np.arange(1, K // 2)
+    assert np.array_equal(got["P"][:, k], got["P"][:, K - k])
+    assert np.all(got["bins"] <= K // 2)
+
+
+def test_optional_outputs_and_set_array_response():
+    cfg = synth.config(1)
+    x = synth.gen_windows_numpy(cfg, 77, 0, 10)
+    hb = music_doa_helper(cfg["m"], cfg["n"], cfg["nsamples"], cfg["resolution"], synth.FREQUENCY, synth.SPACING,
+                          cfg["antenna_array"], output_spectrum=False)
+    ang = np.zeros((10, 1), np.float32)
+    lvl = np.zeros((10, 1), np.float32)
+    assert hb.work(10, [x], [ang, lvl]) == 10
+    t0 = np.asarray(hb.array_response).astype(np.complex64)
+    ref = co.work_batch(x, 4, 1, t0)
+    assert np.array_equal(hb.impl.last_bins(), ref["bins"]) and np.array_equal(ang, ref["angles"])
+    # only port 0 connected (the reference would dereference lvl == NULL here, :147-154)
+    ang2 = np.zeros((10, 1), np.float32)
+    assert hb.impl.work(10, [x], [ang2]) == 10 and np.array_equal(ang2, ang)
+    # retune: new wavelength -> new table (python/music_doa_helper.py:100-103)
+    hb.set_frequency(synth.FREQUENCY * 0.8)
+    t1 = np.asarray(hb.array_response).astype(np.complex64)
+    assert not np.array_equal(t0, t1)
+    assert hb.work(10, [x], [ang, lvl]) == 10
+    ref1 = co.work_batch(x, 4, 1, t1)
+    assert np.array_equal(hb.impl.last_bins(), ref1["bins"]) and np.array_equal(ang, ref1["angles"])
+    assert helpers.rel_err(lvl, ref1["levels"]) <= P_RTOL
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (10k windows of M=4 x 4096 snapshots, 3600 angles) generated
+    on the device: statelessness under permutation, exact invariance to power-of-two scaling,
+    chunking independence, and oracle parity on a random subset."""
+    cfg = synth.config(2)
+    table = helpers.table_for(cfg)
+    seed = synth.BASE_SEED + 2
+    W = cfg["windows"]
+    dev = torch.device("cuda:0")
+    d_in = synth.gen_windows_torch(cfg, seed, 0, W, dev)
+    blk = music_doa(cfg["m"], cfg["n"], cfg["nsamples"], table.tolist(), cfg["resolution"])
+
+    def run(d_x, nw):
+        a = torch.empty((nw, 1), dtype=torch.float32, device=dev)
+        l = torch.empty((nw, 1), dtype=torch.float32, device=dev)
+        b = torch.empty((nw, 1), dtype=torch.int32, device=dev)
+        blk.process_device(d_x.data_ptr(), nw, a.data_ptr(), l.data_ptr(), None, b.data_ptr(),
+                           stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return a.cpu().numpy(), l.cpu().numpy(), b.cpu().numpy()
+
+    ang, lvl, bins = run(d_in, W)
+    assert np.all((bins >= 0) & (bins < cfg["resolution"]))
+    # mirror rule: the lower of (k, K-k) is reported
+    tb = synth.true_bins(cfg, seed, 0, W)[:, 0]
+    folded = np.minimum(tb, (cfg["resolution"] - tb) % cfg["resolution"])
+    assert np.mean(np.abs(bins[:, 0] - folded) <= 2) > 0.99  # estimator sanity at 20 dB
+    # oracle parity on a random subset + first windows
+    rng = np.random.default_rng(0)
+    idx = np.unique(np.concatenate([np.arange(16), rng.integers(0, W, 48)]))
+    x = d_in[torch.from_numpy(idx).to(dev)].cpu().numpy().view(np.complex64)
+    ref = co.work_batch(x, cfg["m"], cfg["n"], table)
+    assert np.array_equal(bins[idx], ref["bins"]) and np.array_equal(ang[idx], ref["angles"])
+    assert helpers.rel_err(lvl[idx], ref["levels"]) <= P_RTOL
+    # permutation: the block is stateless across windows
+    perm = torch.randperm(W, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    a2, l2, b2 = run(d_in[perm].contiguous(), W)
+    p = perm.cpu().numpy()
+    assert np.array_equal(b2, bins[p]) and np.array_equal(l2, lvl[p])
+    # power-of-two scaling: R scales exactly, rotations are identical -> P bit-identical
+    a3, l3, b3 = run((d_in[:2048] * 4.0).contiguous(), 2048)
+    assert np.array_equal(b3, bins[:2048]) and np.array_equal(l3, lvl[:2048])
+    # a sub-range gives the same answers as the full batch (chunking independence)
+    a4, l4, b4 = run(d_in[1234:1234 + 777], 777)
+    assert np.array_equal(b4, bins[1234:2011]) and np.array_equal(l4, lvl[1234:2011])
+    blk.close()
+
+
+def test_full_size_single_windows_configs_3_and_5():
+    for base, W in ((3, 3), (5, 4)):
+        cfg = synth.config(base)
+        table = helpers.table_for(cfg)
+        x = synth.gen_windows_numpy(cfg, synth.BASE_SEED + base, 100, W)
+        ref = co.work_batch(x, cfg["m"], cfg["n"], table)
+        got = run_block(cfg, table, x, spectrum=True, device_path=True, want_internals=True)
+        assert_parity(got, ref, cfg["n"])
