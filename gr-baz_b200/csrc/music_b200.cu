@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -49,6 +50,7 @@ struct music_b200 {
     uint32_t cap_windows = 0;
     double *d_R = nullptr, *d_evals = nullptr, *d_Vt = nullptr, *d_P64 = nullptr;
     bool p64_alloc = false;
+    int cov_tma_stages = 6;  // 0 = LDG tile kernel (MUSIC_B200_COV=ldg), 4 or 6 = TMA ring depth
     bool ws_busy = false;
     // optional per-stage timing (bench.py's roofline leg): events around K1/K2/K3/top-n per chunk
     bool timing = false;
@@ -178,7 +180,15 @@ int run_chunk(music_b200 *h, const float *d_in, uint32_t W, float *d_ang, float 
     cudaEvent_t *tev = timing_events(h);
     if (tev) cudaEventRecord(tev[0], st);
     // K1 covariance
-    if (M % 4 == 0) {
+    if (M == 4 && h->cov_tma_stages > 0) {
+        // persistent, one CTA per SM, per-warp TMA ring (see cov4_tma_kernel)
+        const int stages = h->cov_tma_stages;
+        const size_t smem = 1024 + (size_t)COV_WARPS * stages * COV_CHUNK;
+        const int grid = std::min<int>(h->sm_count, (int)((W + COV_WARPS - 1) / COV_WARPS));
+        if (stages == 6) cov4_tma_kernel<6><<<grid, COV_WARPS * 32, smem, st>>>(d_in, h->d_R, (int)W, N);
+        else cov4_tma_kernel<4><<<grid, COV_WARPS * 32, smem, st>>>(d_in, h->d_R, (int)W, N);
+        h->launches++;
+    } else if (M % 4 == 0) {
         const int T = M / 4;
         const int wpb = 8;
         {
@@ -376,6 +386,13 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
             CU(h, cudaMalloc(&h->table[i].soa, soa_doubles(resolution, m) * sizeof(double)));
         }
         // scan kernels with M = 16 need 32 KiB dynamic smem (< 48 KiB default), nothing to opt in.
+        if (const char *e = getenv("MUSIC_B200_COV")) {  // kernel selection for A/B measurements
+            if (!strcmp(e, "ldg")) h->cov_tma_stages = 0;
+            else if (!strcmp(e, "tma4")) h->cov_tma_stages = 4;
+            else if (!strcmp(e, "tma6")) h->cov_tma_stages = 6;
+        }
+        CU(h, cudaFuncSetAttribute(cov4_tma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 6 * COV_CHUNK));
+        CU(h, cudaFuncSetAttribute(cov4_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 4 * COV_CHUNK));
         return upload_table(h, 0, table_c64, h->streams[0]);
     };
     rc = init();

@@ -158,6 +158,156 @@ __global__ void __launch_bounds__(256) cov_tile_kernel(const float *__restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 (M = 4, the headline shape): TMA-staged covariance.  Persistent CTAs (one per SM), one warp
+// per window, and a private ring of COV_STAGES x COV_CHUNK bytes per warp filled by 1-D bulk
+// async copies (cp.async.bulk, SASS UBLKCP) that complete on mbarriers.  The producer is lane 0
+// of the same warp, so "slot free" is just program order (__syncwarp) and only "slot full"
+// needs a barrier.  The ring runs across window boundaries, i.e. the next window's first
+// chunks are already in flight during the warp-shuffle reduction of the current one.
+// Per snapshot and lane: 2 LDS.128, 8 F2F (exact widening), 32 DFMA into 16 accumulators
+// (Hermitian half of x x^H).  Bytes in flight per SM = 8 warps x (STAGES-1) x 4 KiB.
+// ------------------------------------------------------------------------------------------
+constexpr int COV_CHUNK = 4096;  // bytes per stage = 128 snapshots of 4 antennas
+constexpr int COV_WARPS = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void cov4_accumulate(double (&acc)[16], const float4 a, const float4 b)
+{
+    const double r0 = a.x, i0 = a.y, r1 = a.z, i1 = a.w, r2 = b.x, i2 = b.y, r3 = b.z, i3 = b.w;
+    acc[0] = fma(r0, r0, fma(i0, i0, acc[0]));
+    acc[1] = fma(r1, r1, fma(i1, i1, acc[1]));
+    acc[2] = fma(r2, r2, fma(i2, i2, acc[2]));
+    acc[3] = fma(r3, r3, fma(i3, i3, acc[3]));
+    // R_ij += x_i conj(x_j), i < j
+    acc[4] = fma(r0, r1, fma(i0, i1, acc[4]));    acc[5] = fma(i0, r1, fma(-r0, i1, acc[5]));    // 01
+    acc[6] = fma(r0, r2, fma(i0, i2, acc[6]));    acc[7] = fma(i0, r2, fma(-r0, i2, acc[7]));    // 02
+    acc[8] = fma(r0, r3, fma(i0, i3, acc[8]));    acc[9] = fma(i0, r3, fma(-r0, i3, acc[9]));    // 03
+    acc[10] = fma(r1, r2, fma(i1, i2, acc[10]));  acc[11] = fma(i1, r2, fma(-r1, i2, acc[11]));  // 12
+    acc[12] = fma(r1, r3, fma(i1, i3, acc[12]));  acc[13] = fma(i1, r3, fma(-r1, i3, acc[13]));  // 13
+    acc[14] = fma(r2, r3, fma(i2, i3, acc[14]));  acc[15] = fma(i2, r3, fma(-r2, i3, acc[15]));  // 23
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(COV_WARPS * 32, 1) cov4_tma_kernel(const float *__restrict__ in, double *__restrict__ R,
+                                                                     int W, int N)
+{
+    extern __shared__ __align__(128) unsigned char cov_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(cov_smem) + warp * STAGES;  // first 1 KiB: barriers
+    unsigned char *ring = cov_smem + 1024 + (size_t)warp * STAGES * COV_CHUNK;
+    const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
+
+    const int gw = blockIdx.x * COV_WARPS + warp, total_warps = gridDim.x * COV_WARPS;
+    const size_t win_bytes = (size_t)N * 32;
+    const int cpw = (int)((win_bytes + COV_CHUNK - 1) / COV_CHUNK);  // chunks per window
+    const int nwin = gw < W ? (W - gw + total_warps - 1) / total_warps : 0;
+    const long long total = (long long)nwin * cpw;
+    const unsigned char *src0 = reinterpret_cast<const unsigned char *>(in);
+
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue = [&](long long c) {  // lane 0 only
+        const int j = (int)(c / cpw), q = (int)(c % cpw);
+        const size_t off = (size_t)q * COV_CHUNK;
+        const uint32_t bytes = (uint32_t)min((size_t)COV_CHUNK, win_bytes - off);
+        const int slot = (int)(c % STAGES);
+        const unsigned char *src = src0 + ((size_t)gw + (size_t)j * total_warps) * win_bytes + off;
+        mbar_expect_tx(bar0 + 8 * slot, bytes);
+        bulk_g2s(ring0 + slot * COV_CHUNK, src, bytes, bar0 + 8 * slot);
+    };
+    if (lane == 0)
+        for (long long c = 0; c < total && c < STAGES; ++c) issue(c);
+
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+
+    int q = 0, j = 0, slot = 0;
+    uint32_t parity = 0;
+    for (long long c = 0; c < total; ++c) {
+        while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
+        const size_t off = (size_t)q * COV_CHUNK;
+        const int nsnap = (int)(min((size_t)COV_CHUNK, win_bytes - off) >> 5);
+        const float4 *buf = reinterpret_cast<const float4 *>(ring + (size_t)slot * COV_CHUNK);
+        if (nsnap == COV_CHUNK / 32) {
+            float4 xa[4], xb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                xa[u] = buf[2 * (lane + 32 * u)];
+                xb[u] = buf[2 * (lane + 32 * u) + 1];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cov4_accumulate(acc, xa[u], xb[u]);
+        } else {
+            for (int s = lane; s < nsnap; s += 32) cov4_accumulate(acc, buf[2 * s], buf[2 * s + 1]);
+        }
+        __syncwarp();  // every lane is done reading the slot -> it may be refilled
+        if (lane == 0 && c + STAGES < total) issue(c + STAGES);
+        if (++slot == STAGES) { slot = 0; parity ^= 1; }
+        if (++q == cpw) {
+            q = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+            if (lane == 0) {
+                const double dn = (double)N;
+                double *Rw = R + ((size_t)gw + (size_t)j * total_warps) * 32;
+                Rw[0] = acc[0] / dn;   Rw[1] = 0.0;   // (0,0)
+                Rw[10] = acc[1] / dn;  Rw[11] = 0.0;  // (1,1)
+                Rw[20] = acc[2] / dn;  Rw[21] = 0.0;  // (2,2)
+                Rw[30] = acc[3] / dn;  Rw[31] = 0.0;  // (3,3)
+                int e = 4;
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = a + 1; b < 4; ++b) {
+                        const double re = acc[e] / dn, im = acc[e + 1] / dn;
+                        Rw[2 * (a * 4 + b)] = re;  Rw[2 * (a * 4 + b) + 1] = im;
+                        Rw[2 * (b * 4 + a)] = re;  Rw[2 * (b * 4 + a) + 1] = -im;
+                        e += 2;
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+            ++j;
+        }
+    }
+}
+
 // Generic-M covariance (any 2 <= M <= MAXM, used when M % 4 != 0): one CTA per window, thread
 // (entry e, slice s) accumulates R_ij over snapshots c = s, s+S, ...; slices summed in smem.
 __global__ void __launch_bounds__(256) cov_generic_kernel(const float *__restrict__ in, double *__restrict__ R,
@@ -242,6 +392,16 @@ __device__ __forceinline__ void jacobi_rotate(double (&Ar)[MA][MA], double (&Ai)
     }
 }
 
+// Strict total order used for the ascending sort: by value, NaN last, ties by column index
+// (stable).  A total order makes the ranks a permutation even for NaN eigenvalues, so every
+// output slot is written.
+__device__ __forceinline__ bool eig_before(double wl, int l, double wj, int j)
+{
+    const bool nl = wl != wl, nj = wj != wj;
+    if (nl || nj) return (!nl && nj) || (nl && nj && l < j);
+    return (wl < wj) || (wl == wj && l < j);
+}
+
 // MA = array extent; STATIC: M == MA at compile time, everything unrolled into registers
 // (M = 4); otherwise runtime M <= MA with the matrices in local memory.
 template <int MA, bool STATIC>
@@ -312,7 +472,7 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
         for (int j = 0; j < MA; ++j) {
             int rank = 0;
 #pragma unroll
-            for (int l = 0; l < MA; ++l) rank += (Ar[l][l] < Ar[j][j]) || (l < j && Ar[l][l] == Ar[j][j]);
+            for (int l = 0; l < MA; ++l) rank += eig_before(Ar[l][l], l, Ar[j][j], j);
             ew[rank] = Ar[j][j];
 #pragma unroll
             for (int i = 0; i < MA; ++i) {
@@ -323,7 +483,7 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
     } else {
         for (int j = 0; j < M; ++j) {
             int rank = 0;
-            for (int l = 0; l < M; ++l) rank += (Ar[l][l] < Ar[j][j]) || (l < j && Ar[l][l] == Ar[j][j]);
+            for (int l = 0; l < M; ++l) rank += eig_before(Ar[l][l], l, Ar[j][j], j);
             ew[rank] = Ar[j][j];
             for (int i = 0; i < M; ++i) {
                 vw[2 * (rank * M + i)] = Vr[i][j];
@@ -431,10 +591,17 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const double *__restrict__ s
     __syncthreads();
 
     const bool use_sig = (n < M - n);
-    double bestP[SCAN_B];
+    // Peak-only path (no spectrum output): keep the running minimum of d = ||G^H a||^2 instead of
+    // the maximum of P = 1/d, so the IEEE division leaves the inner loop.  The update rule is
+    // exactly "P_new > P_best" (the reference's strict '>' on strengths, :132): a candidate that
+    // is smaller by more than 2^-50 relative has a strictly larger reciprocal; inside that sliver
+    // the two reciprocals are compared.  d is never negative (direct form is a sum of squares,
+    // complement form is only kept above 2^-7 ||a||^2), NaN fails `d < best`.
+    constexpr bool FAST = ARGMAX && !WRITE_P64 && !WRITE_SPEC;
+    double best[SCAN_B];  // FAST: min d; otherwise: max P
     int bestk[SCAN_B];
 #pragma unroll
-    for (int b = 0; b < SCAN_B; ++b) { bestP[b] = 0.0; bestk[b] = -1; }
+    for (int b = 0; b < SCAN_B; ++b) { best[b] = FAST ? __longlong_as_double(0x7ff0000000000000LL) : 0.0; bestk[b] = -1; }
 
     const int ntiles = (K + TILE - 1) / TILE;
     for (int tile = 0; tile < ntiles; ++tile) {
@@ -453,11 +620,20 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const double *__restrict__ s
             for (int b = 0; b < SCAN_B; ++b) {
                 if (b < nb) {
                     const double d = strength_denominator<MT>(ar, ai, na, sV + b * vsz, M, n, use_sig);
-                    const double P = 1.0 / d;
-                    if (WRITE_SPEC) spectrum[(size_t)(w0 + b) * K + k] = (float)P;
-                    if (WRITE_P64) P64[(size_t)(w0 + b) * K + k] = P;
-                    if (ARGMAX) {
-                        if (P > bestP[b]) { bestP[b] = P; bestk[b] = k; }  // k ascending per thread: strict > keeps the lower bin
+                    if (FAST) {
+                        if (d < best[b]) {
+                            if (d < best[b] * 0.99999999999999911182 /* 1 - 2^-50 */ || 1.0 / d > 1.0 / best[b]) {
+                                best[b] = d;
+                                bestk[b] = k;
+                            }
+                        }
+                    } else {
+                        const double P = 1.0 / d;
+                        if (WRITE_SPEC) spectrum[(size_t)(w0 + b) * K + k] = (float)P;
+                        if (WRITE_P64) P64[(size_t)(w0 + b) * K + k] = P;
+                        if (ARGMAX) {
+                            if (P > best[b]) { best[b] = P; bestk[b] = k; }  // k ascending per thread: strict > keeps the lower bin
+                        }
                     }
                 }
             }
@@ -469,8 +645,8 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const double *__restrict__ s
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
         for (int b = 0; b < SCAN_B; ++b) {
-            double P = bestP[b];
             int kk = bestk[b];
+            double P = FAST ? (kk >= 0 ? 1.0 / best[b] : 0.0) : best[b];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double Po = __shfl_xor_sync(0xffffffffu, P, o);
