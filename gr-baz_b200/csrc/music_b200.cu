@@ -33,6 +33,13 @@ struct DeviceTable {
     double *soa = nullptr;  // [ntiles][2M+1][TILE]
 };
 
+struct Workspace {
+    double *R = nullptr, *ev = nullptr, *Vt = nullptr, *P64 = nullptr;
+    uint32_t cap = 0, p64_cap = 0;
+    cudaEvent_t cov_done = nullptr, scan_done = nullptr;
+    bool used = false;
+};
+
 }  // namespace
 
 struct music_b200 {
@@ -46,12 +53,14 @@ struct music_b200 {
     DeviceTable table[2];
     int cur_table = 0;
 
-    // device workspace, sized for `cap_windows`
-    uint32_t cap_windows = 0;
-    double *d_R = nullptr, *d_evals = nullptr, *d_Vt = nullptr, *d_P64 = nullptr;
-    bool p64_alloc = false;
+    // fp64 workspace slots (R, eigenvalues, sorted eigenvectors, optional strengths) and the two
+    // internal streams of the cov -> eig/scan pipeline
+    Workspace ws[3];
+    cudaStream_t s_cov = nullptr, s_scan = nullptr;
+    cudaEvent_t ev_in = nullptr;
+    bool pipeline = true;    // MUSIC_B200_PIPE=0 disables the sub-batch pipeline
+    bool scan_fast = true;   // MUSIC_B200_SCAN=general disables the specialised n == 1 kernel
     int cov_tma_stages = 6;  // 0 = LDG tile kernel (MUSIC_B200_COV=ldg), 4 or 6 = TMA ring depth
-    bool ws_busy = false;
     // optional per-stage timing (bench.py's roofline leg): events around K1/K2/K3/top-n per chunk
     bool timing = false;
     std::vector<cudaEvent_t> tev;   // 5 events per timed chunk
@@ -107,44 +116,49 @@ int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t s
     return MUSIC_B200_OK;
 }
 
-// Chunk size (windows) bounding the fp64 workspace to ~1 GiB.
-uint32_t pick_chunk(const music_b200 *h, bool need_p64)
+constexpr int NSLOT = 3;           // workspace ring for the cov -> eig/scan software pipeline
+constexpr uint32_t MIN_SUB = 1024; // windows; below 2*MIN_SUB a call is not split
+
+// Windows per sub-batch bounding one workspace slot to ~384 MiB.
+uint32_t max_sub_windows(const music_b200 *h, bool need_p64)
 {
     const size_t per_win = (size_t)h->m * h->m * 2 * 8 * 2 + h->m * 8 + (need_p64 ? (size_t)h->K * 8 : 0);
-    size_t c = ((size_t)1 << 30) / per_win;
+    size_t c = ((size_t)384 << 20) / per_win;
     c = std::max<size_t>(SCAN_B, std::min<size_t>(c, 1u << 20));
     return (uint32_t)(c / SCAN_B * SCAN_B);
 }
 
-int ensure_workspace(music_b200 *h, uint32_t windows, bool need_p64)
+int ensure_slot(music_b200 *h, Workspace &ws, uint32_t windows, bool need_p64)
 {
-    if (windows > h->cap_windows || (need_p64 && !h->p64_alloc)) {
-        const uint32_t cap = std::max(windows, h->cap_windows);
-        cudaFree(h->d_R); cudaFree(h->d_evals); cudaFree(h->d_Vt); cudaFree(h->d_P64);
-        h->d_R = h->d_evals = h->d_Vt = h->d_P64 = nullptr;
-        h->cap_windows = 0; h->p64_alloc = false;
+    if (windows > ws.cap) {
+        // the slot may still be in use by an earlier call on another stream
+        if (ws.used) CU(h, cudaEventSynchronize(ws.scan_done));
+        cudaFree(ws.R); cudaFree(ws.ev); cudaFree(ws.Vt);
+        ws.R = ws.ev = ws.Vt = nullptr; ws.cap = 0;
         const size_t mm = (size_t)h->m * h->m * 2;
-        CU(h, cudaMalloc(&h->d_R, cap * mm * sizeof(double)));
-        CU(h, cudaMalloc(&h->d_Vt, cap * mm * sizeof(double)));
-        CU(h, cudaMalloc(&h->d_evals, (size_t)cap * h->m * sizeof(double)));
-        if (need_p64) {
-            CU(h, cudaMalloc(&h->d_P64, (size_t)cap * h->K * sizeof(double)));
-            h->p64_alloc = true;
-        }
-        h->cap_windows = cap;
+        CU(h, cudaMalloc(&ws.R, windows * mm * sizeof(double)));
+        CU(h, cudaMalloc(&ws.Vt, windows * mm * sizeof(double)));
+        CU(h, cudaMalloc(&ws.ev, (size_t)windows * h->m * sizeof(double)));
+        ws.cap = windows;
+    }
+    if (need_p64 && windows > ws.p64_cap) {
+        if (ws.used) CU(h, cudaEventSynchronize(ws.scan_done));
+        cudaFree(ws.P64); ws.P64 = nullptr; ws.p64_cap = 0;
+        CU(h, cudaMalloc(&ws.P64, (size_t)windows * h->K * sizeof(double)));
+        ws.p64_cap = windows;
     }
     return MUSIC_B200_OK;
 }
 
 template <int MT>
-void launch_scan(music_b200 *h, const double *soa, uint32_t W, bool argmax, bool p64, bool spec, PeakOut po,
-                 float *d_spec, double *d_p64, cudaStream_t st)
+void launch_scan(music_b200 *h, const Workspace &ws, const double *soa, uint32_t W, bool argmax, bool p64, bool spec,
+                 PeakOut po, float *d_spec, double *d_p64, cudaStream_t st)
 {
     const int grid = (W + SCAN_B - 1) / SCAN_B;
     const size_t smem = (size_t)SCAN_B * h->m * h->m * 2 * sizeof(double);
 #define SCAN_CASE(A, P, S)                                                                              \
     if (argmax == A && p64 == P && spec == S)                                                           \
-        scan_kernel<MT, A, P, S><<<grid, TILE, smem, st>>>(soa, h->d_Vt, (int)h->m, (int)h->n, (int)h->K, \
+        scan_kernel<MT, A, P, S><<<grid, TILE, smem, st>>>(soa, ws.Vt, (int)h->m, (int)h->n, (int)h->K,  \
                                                            (int)W, po, d_spec, d_p64);
     SCAN_CASE(true, false, false)
     SCAN_CASE(true, false, true)
@@ -171,66 +185,76 @@ cudaEvent_t *timing_events(music_b200 *h)
     return p;
 }
 
-// One chunk (<= cap_windows) entirely on `st`.
-int run_chunk(music_b200 *h, const float *d_in, uint32_t W, float *d_ang, float *d_lvl, float *d_spec,
-              int32_t *d_bins, double *d_P64_out, double *d_R_out, double *d_ev_out, cudaStream_t st)
+// K1: covariance of W windows into ws.R, on `st`.
+void launch_cov(music_b200 *h, const Workspace &ws, const float *d_in, uint32_t W, cudaStream_t st)
 {
     const int M = (int)h->m, N = (int)h->N;
-    const double *soa = h->table[h->cur_table].soa;
-    cudaEvent_t *tev = timing_events(h);
-    if (tev) cudaEventRecord(tev[0], st);
-    // K1 covariance
     if (M == 4 && h->cov_tma_stages > 0) {
         // persistent, one CTA per SM, per-warp TMA ring (see cov4_tma_kernel)
         const int stages = h->cov_tma_stages;
         const size_t smem = 1024 + (size_t)COV_WARPS * stages * COV_CHUNK;
         const int grid = std::min<int>(h->sm_count, (int)((W + COV_WARPS - 1) / COV_WARPS));
-        if (stages == 6) cov4_tma_kernel<6><<<grid, COV_WARPS * 32, smem, st>>>(d_in, h->d_R, (int)W, N);
-        else cov4_tma_kernel<4><<<grid, COV_WARPS * 32, smem, st>>>(d_in, h->d_R, (int)W, N);
+        if (stages == 6) cov4_tma_kernel<6><<<grid, COV_WARPS * 32, smem, st>>>(d_in, ws.R, (int)W, N);
+        else cov4_tma_kernel<4><<<grid, COV_WARPS * 32, smem, st>>>(d_in, ws.R, (int)W, N);
         h->launches++;
     } else if (M % 4 == 0) {
         const int T = M / 4;
         const int wpb = 8;
         {
             const long long items = (long long)W * T;
-            cov_tile_kernel<false><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, h->d_R, (int)W, N, M);
+            cov_tile_kernel<false><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, ws.R, (int)W, N, M);
             h->launches++;
         }
         if (T > 1) {
             const long long items = (long long)W * (T * (T - 1) / 2);
-            cov_tile_kernel<true><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, h->d_R, (int)W, N, M);
+            cov_tile_kernel<true><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, ws.R, (int)W, N, M);
             h->launches++;
         }
     } else {
         const int E = M * (M + 1) / 2;
         const int S = 256 / E;
-        cov_generic_kernel<<<W, 256, (size_t)S * E * 2 * sizeof(double), st>>>(d_in, h->d_R, (int)W, N, M);
+        cov_generic_kernel<<<W, 256, (size_t)S * E * 2 * sizeof(double), st>>>(d_in, ws.R, (int)W, N, M);
         h->launches++;
     }
-    if (tev) cudaEventRecord(tev[1], st);
-    // K2 eigendecomposition
+}
+
+// K2 + K3 (+ top-n) of W windows from ws.R, on `st`.  tev (optional) = timing events [1..4].
+int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, float *d_ang, float *d_lvl, float *d_spec,
+                    int32_t *d_bins, double *d_P64_out, double *d_R_out, double *d_ev_out, cudaStream_t st,
+                    cudaEvent_t *tev)
+{
+    const int M = (int)h->m;
+    const double *soa = h->table[h->cur_table].soa;
     {
         const int grid = (W + 127) / 128;
         switch (M) {
-        case 4: eig_kernel<4, true><<<grid, 128, 0, st>>>(h->d_R, h->d_evals, h->d_Vt, M, (int)W); break;
+        case 4: eig_kernel<4, true><<<grid, 128, 0, st>>>(ws.R, ws.ev, ws.Vt, M, (int)W); break;
         default:
-            if (M <= 8) eig_kernel<8, false><<<grid, 128, 0, st>>>(h->d_R, h->d_evals, h->d_Vt, M, (int)W);
-            else eig_kernel<MAXM, false><<<grid, 128, 0, st>>>(h->d_R, h->d_evals, h->d_Vt, M, (int)W);
+            if (M <= 8) eig_kernel<8, false><<<grid, 128, 0, st>>>(ws.R, ws.ev, ws.Vt, M, (int)W);
+            else eig_kernel<MAXM, false><<<grid, 128, 0, st>>>(ws.R, ws.ev, ws.Vt, M, (int)W);
             break;
         }
         h->launches++;
     }
     if (tev) cudaEventRecord(tev[2], st);
-    // K3 scan (+ top-n)
     const bool argmax = (h->n == 1);
     const bool need_p64 = !argmax || d_P64_out != nullptr;
-    double *p64 = d_P64_out ? d_P64_out : h->d_P64;
+    double *p64 = d_P64_out ? d_P64_out : ws.P64;
     PeakOut po{d_ang, d_lvl, d_bins};
-    switch (M) {
-    case 4: launch_scan<4>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
-    case 8: launch_scan<8>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
-    case 16: launch_scan<16>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
-    default: launch_scan<0>(h, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+    const bool fast = argmax && !need_p64 && !d_spec && (M == 4 || M == 8 || M == 16) && h->scan_fast;
+    if (fast) {
+        const int grid = (W + SCAN_B - 1) / SCAN_B;
+        if (M == 4) scan_peak1_kernel<4><<<grid, TILE, 0, st>>>(soa, ws.Vt, (int)h->K, (int)W, po);
+        else if (M == 8) scan_peak1_kernel<8><<<grid, TILE, 0, st>>>(soa, ws.Vt, (int)h->K, (int)W, po);
+        else scan_peak1_kernel<16><<<grid, TILE, 0, st>>>(soa, ws.Vt, (int)h->K, (int)W, po);
+        h->launches++;
+    } else {
+        switch (M) {
+        case 4: launch_scan<4>(h, ws, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+        case 8: launch_scan<8>(h, ws, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+        case 16: launch_scan<16>(h, ws, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+        default: launch_scan<0>(h, ws, soa, W, argmax, need_p64, d_spec != nullptr, po, d_spec, p64, st); break;
+        }
     }
     if (tev) cudaEventRecord(tev[3], st);
     if (!argmax) {
@@ -239,37 +263,67 @@ int run_chunk(music_b200 *h, const float *d_in, uint32_t W, float *d_ang, float 
     }
     if (tev) cudaEventRecord(tev[4], st);
     if (d_R_out)
-        CU(h, cudaMemcpyAsync(d_R_out, h->d_R, (size_t)W * M * M * 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaMemcpyAsync(d_R_out, ws.R, (size_t)W * M * M * 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (d_ev_out)
-        CU(h, cudaMemcpyAsync(d_ev_out, h->d_evals, (size_t)W * M * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaMemcpyAsync(d_ev_out, ws.ev, (size_t)W * M * sizeof(double), cudaMemcpyDeviceToDevice, st));
     CU(h, cudaGetLastError());
     return MUSIC_B200_OK;
 }
 
-int process_device_locked(music_b200 *h, const float *d_in, uint32_t nwindows, float *d_ang, float *d_lvl,
-                          float *d_spec, int32_t *d_bins, double *d_P64, double *d_R, double *d_ev,
-                          cudaStream_t st)
+// Enqueue `nwindows` windows.  Large calls are cut into sub-batches and software-pipelined over
+// two internal streams: K1 (HBM-bound, FP64 pipe ~1/3 busy) of sub-batch j+1 runs concurrently
+// with K2+K3 (FP64-only) of sub-batch j, each sub-batch owning one workspace slot.  `st` is
+// ordered before the first and after the last piece of work.  Small calls, and calls made while
+// stage timing is on, run serially on `st`.
+int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d_ang, float *d_lvl, float *d_spec,
+                   int32_t *d_bins, double *d_P64, double *d_R, double *d_ev, cudaStream_t st, int first_slot,
+                   bool allow_pipeline)
 {
     if (nwindows == 0) return MUSIC_B200_OK;
     if (!d_in || !d_ang) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 and d_angles must not be NULL");
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 must be 16-byte aligned");
     const bool internal_p64 = (h->n != 1) && !d_P64;
-    const uint32_t chunk = pick_chunk(h, internal_p64);
-    int rc = ensure_workspace(h, std::min(chunk, (nwindows + SCAN_B - 1) / SCAN_B * SCAN_B), internal_p64);
-    if (rc) return rc;
-    // The fp64 workspace is per handle: order this call after the previous one even if the
-    // caller switched streams.
-    if (h->ws_busy) CU(h, cudaStreamWaitEvent(st, h->done[0], 0));
-    for (uint32_t w0 = 0; w0 < nwindows; w0 += chunk) {
-        const uint32_t W = std::min(chunk, nwindows - w0);
-        rc = run_chunk(h, d_in + (size_t)w0 * h->nsamples * 2, W, d_ang + (size_t)w0 * h->n,
-                       d_lvl ? d_lvl + (size_t)w0 * h->n : nullptr, d_spec ? d_spec + (size_t)w0 * h->K : nullptr,
-                       d_bins ? d_bins + (size_t)w0 * h->n : nullptr, d_P64 ? d_P64 + (size_t)w0 * h->K : nullptr,
-                       d_R ? d_R + (size_t)w0 * h->m * h->m * 2 : nullptr, d_ev ? d_ev + (size_t)w0 * h->m : nullptr, st);
-        if (rc) return rc;
+    const uint32_t max_sub = max_sub_windows(h, internal_p64);
+    const bool pipe = allow_pipeline && h->pipeline && !h->timing && nwindows >= 2 * MIN_SUB;
+    uint32_t sub;
+    if (pipe) {
+        const uint32_t nsub = std::min<uint32_t>(8, std::max<uint32_t>(2, nwindows / MIN_SUB));
+        sub = ((nwindows + nsub - 1) / nsub + SCAN_B - 1) / SCAN_B * SCAN_B;
+        sub = std::min(sub, max_sub);
+    } else {
+        sub = std::min((nwindows + SCAN_B - 1) / SCAN_B * SCAN_B, max_sub);
     }
-    CU(h, cudaEventRecord(h->done[0], st));
-    h->ws_busy = true;
+    cudaStream_t s_cov = pipe ? h->s_cov : st, s_scan = pipe ? h->s_scan : st;
+    if (pipe) {
+        CU(h, cudaEventRecord(h->ev_in, st));
+        CU(h, cudaStreamWaitEvent(s_cov, h->ev_in, 0));
+    }
+    int slot = first_slot, last_slot = -1;
+    for (uint32_t w0 = 0; w0 < nwindows; w0 += sub) {
+        const uint32_t W = std::min(sub, nwindows - w0);
+        Workspace &ws = h->ws[slot];
+        int rc = ensure_slot(h, ws, sub, internal_p64);
+        if (rc) return rc;
+        if (ws.used) CU(h, cudaStreamWaitEvent(s_cov, ws.scan_done, 0));  // slot free again
+        cudaEvent_t *tev = timing_events(h);
+        if (tev) cudaEventRecord(tev[0], s_cov);
+        launch_cov(h, ws, d_in + (size_t)w0 * h->nsamples * 2, W, s_cov);
+        if (tev) cudaEventRecord(tev[1], s_cov);
+        if (pipe) {
+            CU(h, cudaEventRecord(ws.cov_done, s_cov));
+            CU(h, cudaStreamWaitEvent(s_scan, ws.cov_done, 0));
+        }
+        rc = launch_eig_scan(h, ws, W, d_ang + (size_t)w0 * h->n, d_lvl ? d_lvl + (size_t)w0 * h->n : nullptr,
+                             d_spec ? d_spec + (size_t)w0 * h->K : nullptr, d_bins ? d_bins + (size_t)w0 * h->n : nullptr,
+                             d_P64 ? d_P64 + (size_t)w0 * h->K : nullptr, d_R ? d_R + (size_t)w0 * h->m * h->m * 2 : nullptr,
+                             d_ev ? d_ev + (size_t)w0 * h->m : nullptr, s_scan, tev);
+        if (rc) return rc;
+        CU(h, cudaEventRecord(ws.scan_done, s_scan));
+        ws.used = true;
+        last_slot = slot;
+        slot = pipe ? (slot + 1) % NSLOT : slot;
+    }
+    if (pipe && last_slot >= 0) CU(h, cudaStreamWaitEvent(st, h->ws[last_slot].scan_done, 0));
     return MUSIC_B200_OK;
 }
 
@@ -385,12 +439,21 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
             CU(h, cudaMalloc(&h->table[i].c64, (size_t)resolution * m * 2 * sizeof(float)));
             CU(h, cudaMalloc(&h->table[i].soa, soa_doubles(resolution, m) * sizeof(double)));
         }
+        CU(h, cudaStreamCreateWithFlags(&h->s_cov, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->s_scan, cudaStreamNonBlocking));
+        CU(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+        for (int i = 0; i < NSLOT; ++i) {
+            CU(h, cudaEventCreateWithFlags(&h->ws[i].cov_done, cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->ws[i].scan_done, cudaEventDisableTiming));
+        }
+        if (const char *e = getenv("MUSIC_B200_PIPE")) h->pipeline = atoi(e) != 0;
         // scan kernels with M = 16 need 32 KiB dynamic smem (< 48 KiB default), nothing to opt in.
         if (const char *e = getenv("MUSIC_B200_COV")) {  // kernel selection for A/B measurements
             if (!strcmp(e, "ldg")) h->cov_tma_stages = 0;
             else if (!strcmp(e, "tma4")) h->cov_tma_stages = 4;
             else if (!strcmp(e, "tma6")) h->cov_tma_stages = 6;
         }
+        if (const char *e = getenv("MUSIC_B200_SCAN")) h->scan_fast = strcmp(e, "general") != 0;
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 6 * COV_CHUNK));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 4 * COV_CHUNK));
         return upload_table(h, 0, table_c64, h->streams[0]);
@@ -430,8 +493,8 @@ int music_b200_process_device_ex(music_b200 *h, const float *d_in_c64, uint32_t 
     if (!h) return MUSIC_B200_EINVAL;
     std::lock_guard<std::mutex> g(h->mutex);
     CU(h, cudaSetDevice(h->device));
-    return process_device_locked(h, d_in_c64, nwindows, d_angles, d_levels, d_spectrum, d_bins, d_P64, d_R, d_eigvals,
-                                 static_cast<cudaStream_t>(stream));
+    return enqueue_device(h, d_in_c64, nwindows, d_angles, d_levels, d_spectrum, d_bins, d_P64, d_R, d_eigvals,
+                          static_cast<cudaStream_t>(stream), 0, true);
 }
 
 int music_b200_process_device(music_b200 *h, const float *d_in_c64, uint32_t nwindows, float *d_angles,
@@ -456,14 +519,9 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
     chunk = std::max<uint32_t>(1, chunk);
     int rc = ensure_host_staging(h, chunk, spectrum != nullptr);
     if (rc) return rc;
-    // the two stream slots share the fp64 workspace, so kernels of slot i+1 must follow slot i:
-    // chain them with events; copies still overlap.
-    const bool internal_p64 = (h->n != 1);
-    rc = ensure_workspace(h, (chunk + SCAN_B - 1) / SCAN_B * SCAN_B, internal_p64);
-    if (rc) return rc;
+    // Each of the two copy streams computes in its own workspace slot, so H2D, kernels and D2H of
+    // consecutive chunks overlap freely (the path is PCIe-bound by ~100x, no sub-batch pipeline).
     int it = 0;
-    cudaEvent_t compute_done[2];
-    for (int i = 0; i < 2; ++i) CU(h, cudaEventCreateWithFlags(&compute_done[i], cudaEventDisableTiming));
     rc = MUSIC_B200_OK;
     for (uint32_t w0 = 0; w0 < nwindows && rc == MUSIC_B200_OK; w0 += chunk, ++it) {
         const int s = it & 1;
@@ -471,11 +529,9 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
         cudaStream_t st = h->streams[s];
         if (it >= 2) CU(h, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
         CU(h, cudaMemcpyAsync(h->d_in[s], in_c64 + (size_t)w0 * h->nsamples * 2, (size_t)W * win_bytes, cudaMemcpyHostToDevice, st));
-        if (it >= 1) CU(h, cudaStreamWaitEvent(st, compute_done[s ^ 1], 0));  // workspace hand-over
-        rc = run_chunk(h, h->d_in[s], W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
-                       nullptr, nullptr, nullptr, st);
+        rc = enqueue_device(h, h->d_in[s], W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
+                            nullptr, nullptr, nullptr, st, s, false);
         if (rc) break;
-        CU(h, cudaEventRecord(compute_done[s], st));
         CU(h, cudaMemcpyAsync(angles + (size_t)w0 * h->n, h->d_ang[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (levels) CU(h, cudaMemcpyAsync(levels + (size_t)w0 * h->n, h->d_lvl[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (bins) CU(h, cudaMemcpyAsync(bins + (size_t)w0 * h->n, h->d_bins[s], (size_t)W * h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -483,7 +539,6 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
     }
     cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
     cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
-    for (int i = 0; i < 2; ++i) cudaEventDestroy(compute_done[i]);
     if (rc) return rc;
     if (e0 != cudaSuccess || e1 != cudaSuccess)
         return fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
@@ -496,7 +551,15 @@ void music_b200_destroy(music_b200 *h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     free_host_staging(h);
-    cudaFree(h->d_R); cudaFree(h->d_evals); cudaFree(h->d_Vt); cudaFree(h->d_P64);
+    for (int i = 0; i < NSLOT; ++i) {
+        Workspace &ws = h->ws[i];
+        cudaFree(ws.R); cudaFree(ws.ev); cudaFree(ws.Vt); cudaFree(ws.P64);
+        if (ws.cov_done) cudaEventDestroy(ws.cov_done);
+        if (ws.scan_done) cudaEventDestroy(ws.scan_done);
+    }
+    if (h->s_cov) cudaStreamDestroy(h->s_cov);
+    if (h->s_scan) cudaStreamDestroy(h->s_scan);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->table[i].c64); cudaFree(h->table[i].soa);
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);

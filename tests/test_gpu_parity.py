@@ -163,8 +163,13 @@ def test_mirror_ties_resolve_to_lower_bin():
     got = run_block(cfg, table, x, spectrum=True, device_path=True, want_internals=True)
     K = cfg["resolution"]
     k = np.arange(1, K // 2)
+    k = k[np.all(table[k] == table[K - k], axis=1)]  # rows 90/270 and 120/240 differ in the c64 rounding of ~1e-16
+    assert len(k) >= K // 2 - 4
     assert np.array_equal(got["P"][:, k], got["P"][:, K - k])
     assert np.all(got["bins"] <= K // 2)
+    # the fused peak-only kernel (no spectrum/P64 requested) picks the same bins
+    got2 = run_block(cfg, table, x, spectrum=False, device_path=True)
+    assert np.array_equal(got2["bins"], got["bins"]) and np.array_equal(got2["levels"], got["levels"])
 
 
 def test_optional_outputs_and_set_array_response():

@@ -8,10 +8,14 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
 echo "== smoke" ; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log; tail -3 $OUT/smoke.log
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log; tail -15 $OUT/pytest_gpu.log
-for cov in ldg tma4 tma6; do
-  echo "== bench cov=$cov"; MUSIC_B200_COV=$cov timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_$cov.json 2> $OUT/bench_$cov.err; python - <<PY
+for var in "MUSIC_B200_PIPE=0" "MUSIC_B200_PIPE=1" "MUSIC_B200_PIPE=1 MUSIC_B200_COV=tma4" "MUSIC_B200_PIPE=0 MUSIC_B200_SCAN=general" ${EXTRA_VARIANTS}; do
+  tag=$(echo "$var" | tr ' =' '__')
+  echo "== bench $var"; env $var timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_$tag.json 2> $OUT/bench_$tag.err; python - <<PY
 import json
-d=json.load(open("$OUT/bench_$cov.json")); print("$cov", "value=%.3e"%d["value"], "ms/step=%.4f"%d["ms_per_step"], d["stages"], "roof=%.3f whole=%.3f"%(d["roofline"]["frac"], d["roofline"]["whole_step_frac"]), d["clocks"])
+try:
+    d=json.load(open("$OUT/bench_$tag.json")); print("$var", "value=%.3e"%d["value"], "ms/step=%.4f"%d["ms_per_step"], d["stages"], "roof=%.3f whole=%.3f"%(d["roofline"]["frac"], d["roofline"]["whole_step_frac"]), d["clocks"])
+except Exception as e:
+    print("$var FAILED", e); print(open("$OUT/bench_$tag.err").read()[-2000:])
 PY
 done
 echo "== bench (default)"; timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -5 $OUT/bench.err
