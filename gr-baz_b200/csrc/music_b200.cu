@@ -58,7 +58,7 @@ struct music_b200 {
     Workspace ws[3];
     cudaStream_t s_cov = nullptr, s_scan = nullptr;
     cudaEvent_t ev_in = nullptr;
-    bool pipeline = true;    // MUSIC_B200_PIPE=0 disables the sub-batch pipeline
+    bool pipeline = false;   // MUSIC_B200_PIPE=1 enables the sub-batch pipeline (launch-bound at 10k windows: off)
     bool scan_fast = true;   // MUSIC_B200_SCAN=general disables the specialised n == 1 kernel
     int cov_tma_stages = 6;  // 0 = LDG tile kernel (MUSIC_B200_COV=ldg), 4 or 6 = TMA ring depth
     // optional per-stage timing (bench.py's roofline leg): events around K1/K2/K3/top-n per chunk

@@ -402,6 +402,16 @@ __device__ __forceinline__ bool eig_before(double wl, int l, double wj, int j)
     return (wl < wj) || (wl == wj && l < j);
 }
 
+// Unit phasor p = conj(v0)/|v0| that makes component 0 of an eigenvector real and >= 0 (any
+// phase is a valid eigenvector; MUSIC only uses |e^H a| and the projector).  The scan kernels
+// rely on Im(v0) == 0 to drop two multiply-adds per bin.
+__device__ __forceinline__ void eig_phase(double v0r, double v0i, double &pr, double &pi)
+{
+    const double mag = sqrt(v0r * v0r + v0i * v0i);
+    if (mag > 0.0) { pr = v0r / mag; pi = -v0i / mag; }
+    else { pr = 1.0; pi = 0.0; }  // v0 == 0 (or NaN): leave the vector as it is
+}
+
 // MA = array extent; STATIC: M == MA at compile time, everything unrolled into registers
 // (M = 4); otherwise runtime M <= MA with the matrices in local memory.
 template <int MA, bool STATIC>
@@ -474,10 +484,12 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
 #pragma unroll
             for (int l = 0; l < MA; ++l) rank += eig_before(Ar[l][l], l, Ar[j][j], j);
             ew[rank] = Ar[j][j];
+            double pr, pi;
+            eig_phase(Vr[0][j], Vi[0][j], pr, pi);
 #pragma unroll
             for (int i = 0; i < MA; ++i) {
-                vw[2 * (rank * MA + i)] = Vr[i][j];
-                vw[2 * (rank * MA + i) + 1] = Vi[i][j];
+                vw[2 * (rank * MA + i)] = Vr[i][j] * pr - Vi[i][j] * pi;
+                vw[2 * (rank * MA + i) + 1] = (i == 0) ? 0.0 : Vr[i][j] * pi + Vi[i][j] * pr;
             }
         }
     } else {
@@ -485,9 +497,11 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
             int rank = 0;
             for (int l = 0; l < M; ++l) rank += eig_before(Ar[l][l], l, Ar[j][j], j);
             ew[rank] = Ar[j][j];
+            double pr, pi;
+            eig_phase(Vr[0][j], Vi[0][j], pr, pi);
             for (int i = 0; i < M; ++i) {
-                vw[2 * (rank * M + i)] = Vr[i][j];
-                vw[2 * (rank * M + i) + 1] = Vi[i][j];
+                vw[2 * (rank * M + i)] = Vr[i][j] * pr - Vi[i][j] * pi;
+                vw[2 * (rank * M + i) + 1] = (i == 0) ? 0.0 : Vr[i][j] * pi + Vi[i][j] * pr;
             }
         }
     }
@@ -729,10 +743,11 @@ __global__ void __launch_bounds__(TILE) scan_peak1_kernel(const double *__restri
     __syncthreads();
 
     const uint32_t sV0 = smem_u32(sV);
-    long long bestb[SCAN_B];  // bit pattern of the running minimum d
+    double bestd[SCAN_B];     // running minimum of d
+    unsigned hbm1[SCAN_B];    // high word of bestd, minus one (saturating at 0): screening threshold
     int bestk[SCAN_B];
 #pragma unroll
-    for (int b = 0; b < SCAN_B; ++b) { bestb[b] = 0x7ff0000000000000LL; bestk[b] = -1; }
+    for (int b = 0; b < SCAN_B; ++b) { bestd[b] = __longlong_as_double(0x7ff0000000000000LL); hbm1[b] = 0x7fefffffu; bestk[b] = -1; }
 
     const int ntiles = (K + TILE - 1) / TILE;
     for (int tile = 0; tile < ntiles; ++tile) {
@@ -746,42 +761,51 @@ __global__ void __launch_bounds__(TILE) scan_peak1_kernel(const double *__restri
         }
         const double na = tb[(size_t)(2 * M) * TILE];
         const double gna = COMPLEMENT_GUARD * na;
+        const int hg = __double2hiint(gna);
         double d[SCAN_B];
         bool slow = false;
 #pragma unroll
         for (int b = 0; b < SCAN_B; ++b) {
             const uint32_t e = sV0 + 8 * (b * vsz + 2 * (M - 1) * M);  // signal vector = largest eigenvalue
-            double cr = 0.0, ci = 0.0;
+            // component 0 of every eigenvector is real (eig_kernel fixes the phase): 2 DMUL, not 4 DFMA
+            const double2 e0 = lds_f64x2(e);
+            double cr = e0.x * ar[0], ci = e0.x * ai[0];
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
+            for (int i = 1; i < M; ++i) {
                 const double2 ev = lds_f64x2(e + 16 * i);
                 cr = fma(ev.x, ar[i], fma(ev.y, ai[i], cr));
                 ci = fma(ev.x, ai[i], fma(-ev.y, ar[i], ci));
             }
             d[b] = fma(-cr, cr, fma(-ci, ci, na));
-            slow |= (d[b] < gna);
+            // screen on the high words (ALU pipe): negative d and anything within one high-word
+            // step of the guard go to the exact test below
+            slow |= (__double2hiint(d[b]) <= hg);
         }
         if (slow) {
 #pragma unroll
             for (int b = 0; b < SCAN_B; ++b)
                 if (d[b] < gna) d[b] = direct_denominator<M>(ar, ai, sV0 + 8 * b * vsz);
         }
-        bool sliver = false;
+        // Running minimum.  Screen on the high 32 bits (sign, exponent, top 20 mantissa bits;
+        // unsigned, so NaNs and negative-signed values sort last): hd < hi(best) - 1 means d is below
+        // the minimum by at least 2^-20 relative - accept.  hd in {hi(best)-1, hi(best)} is ambiguous
+        // (includes exact ties) and is settled exactly, once per tile, in the cold block.
+        bool amb = false;
 #pragma unroll
         for (int b = 0; b < SCAN_B; ++b) {
-            const long long db = __double_as_longlong(d[b]);
-            const long long diff = bestb[b] - db;  // > 0: d is below the running minimum
-            const bool ok = db >= 0;               // sign clear: not a negative-signed NaN
-            if (ok && diff > 8) { bestb[b] = db; bestk[b] = k; }
-            sliver |= ok && ((unsigned long long)(diff - 1) < 8ull);
+            const unsigned hd = (unsigned)__double2hiint(d[b]);
+            amb |= (hd - hbm1[b]) <= 1u;
+            if (hd < hbm1[b]) { bestd[b] = d[b]; bestk[b] = k; hbm1[b] = max(hd, 1u) - 1u; }
         }
-        if (sliver) {
+        if (amb) {
 #pragma unroll
             for (int b = 0; b < SCAN_B; ++b) {
-                const long long db = __double_as_longlong(d[b]);
-                const long long diff = bestb[b] - db;
-                if (db >= 0 && (unsigned long long)(diff - 1) < 8ull) {
-                    if (1.0 / d[b] > 1.0 / __longlong_as_double(bestb[b])) { bestb[b] = db; bestk[b] = k; }
+                if (d[b] < bestd[b]) {  // exactly the reference's rule: replace iff 1/d > 1/best (:132)
+                    if (d[b] < bestd[b] * 0.99999999999999911182 /* 1 - 2^-50 */ || 1.0 / d[b] > 1.0 / bestd[b]) {
+                        bestd[b] = d[b];
+                        bestk[b] = k;
+                        hbm1[b] = max((unsigned)__double2hiint(d[b]), 1u) - 1u;
+                    }
                 }
             }
         }
@@ -792,7 +816,7 @@ __global__ void __launch_bounds__(TILE) scan_peak1_kernel(const double *__restri
 #pragma unroll
     for (int b = 0; b < SCAN_B; ++b) {
         int kk = bestk[b];
-        double P = kk >= 0 ? 1.0 / __longlong_as_double(bestb[b]) : 0.0;
+        double P = kk >= 0 ? 1.0 / bestd[b] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double Po = __shfl_xor_sync(0xffffffffu, P, o);
