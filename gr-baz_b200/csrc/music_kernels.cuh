@@ -728,9 +728,31 @@ __device__ __forceinline__ double direct_denominator(const double *ar, const dou
     return acc;
 }
 
+// Thread mapping: 256 threads = SCAN_G window groups x SCAN_BINS bins; a thread owns one bin of
+// the current 128-bin half tile and SCAN_WPT windows (state in registers), so that 3-4 CTAs fit
+// per SM and every SMSP has >= 6 warps of independent DFMA chains to hide the FP64 latency.
+constexpr int SCAN_WPT = 4;                   // windows per thread
+constexpr int SCAN_G = SCAN_B / SCAN_WPT;     // window groups per CTA
+constexpr int SCAN_BINS = TILE / SCAN_G;      // bins per CTA iteration
+
 template <int M>
-__global__ void __launch_bounds__(TILE) scan_peak1_kernel(const double *__restrict__ soa, const double *__restrict__ Vt,
-                                                          int K, int W, PeakOut out)
+__device__ __forceinline__ double complement_denominator(const double *ar, const double *ai, double na, uint32_t e)
+{
+    // component 0 of every eigenvector is real (eig_kernel fixes the phase): 2 DMUL, not 4 DFMA
+    const double2 e0 = lds_f64x2(e);
+    double cr = e0.x * ar[0], ci = e0.x * ai[0];
+#pragma unroll
+    for (int i = 1; i < M; ++i) {
+        const double2 ev = lds_f64x2(e + 16 * i);
+        cr = fma(ev.x, ar[i], fma(ev.y, ai[i], cr));
+        ci = fma(ev.x, ai[i], fma(-ev.y, ar[i], ci));
+    }
+    return fma(-cr, cr, fma(-ci, ci, na));
+}
+
+template <int M>
+__global__ void __launch_bounds__(TILE, 3) scan_peak1_kernel(const double *__restrict__ soa, const double *__restrict__ Vt,
+                                                             int K, int W, PeakOut out)
 {
     constexpr int vsz = M * M * 2;
     __shared__ __align__(16) double sV[SCAN_B * vsz];
@@ -742,17 +764,18 @@ __global__ void __launch_bounds__(TILE) scan_peak1_kernel(const double *__restri
     }
     __syncthreads();
 
-    const uint32_t sV0 = smem_u32(sV);
-    double bestd[SCAN_B];     // running minimum of d
-    unsigned hbm1[SCAN_B];    // high word of bestd, minus one (saturating at 0): screening threshold
-    int bestk[SCAN_B];
+    const int g = threadIdx.x / SCAN_BINS, t = threadIdx.x % SCAN_BINS;
+    const uint32_t sVg = smem_u32(sV) + 8 * (g * SCAN_WPT * vsz);  // this thread's first window
+    double bestd[SCAN_WPT];     // running minimum of d
+    unsigned hbm1[SCAN_WPT];    // high word of bestd, minus one (saturating at 0): screening threshold
+    int bestk[SCAN_WPT];
 #pragma unroll
-    for (int b = 0; b < SCAN_B; ++b) { bestd[b] = __longlong_as_double(0x7ff0000000000000LL); hbm1[b] = 0x7fefffffu; bestk[b] = -1; }
+    for (int b = 0; b < SCAN_WPT; ++b) { bestd[b] = __longlong_as_double(0x7ff0000000000000LL); hbm1[b] = 0x7fefffffu; bestk[b] = -1; }
 
-    const int ntiles = (K + TILE - 1) / TILE;
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int k = tile * TILE + threadIdx.x;
-        const double *tb = soa + (size_t)tile * (2 * M + 1) * TILE + threadIdx.x;
+    const int niter = (K + SCAN_BINS - 1) / SCAN_BINS;
+    for (int it = 0; it < niter; ++it) {
+        const int k = it * SCAN_BINS + t;  // table is padded to a multiple of TILE with ||a||^2 = +inf
+        const double *tb = soa + (size_t)(k / TILE) * (2 * M + 1) * TILE + (k % TILE);
         double ar[M], ai[M];
 #pragma unroll
         for (int i = 0; i < M; ++i) {
@@ -762,59 +785,45 @@ __global__ void __launch_bounds__(TILE) scan_peak1_kernel(const double *__restri
         const double na = tb[(size_t)(2 * M) * TILE];
         const double gna = COMPLEMENT_GUARD * na;
         const int hg = __double2hiint(gna);
-        double d[SCAN_B];
-        bool slow = false;
+        // Hot loop: d by the complement form, then a screen on the high 32 bits of d (ALU pipe):
+        //   hd <= hi(guard)              -> maybe inside the cancellation guard (or negative): cold
+        //   hd <  hi(best) - 1 (unsigned) -> below the running minimum by >= 2^-20 relative: accept
+        //   hd in {hi(best)-1, hi(best)}  -> ambiguous (includes exact ties): cold
+        // NaNs and negative-signed values are large as unsigned and are never accepted.
+        unsigned cold = 0;
 #pragma unroll
-        for (int b = 0; b < SCAN_B; ++b) {
-            const uint32_t e = sV0 + 8 * (b * vsz + 2 * (M - 1) * M);  // signal vector = largest eigenvalue
-            // component 0 of every eigenvector is real (eig_kernel fixes the phase): 2 DMUL, not 4 DFMA
-            const double2 e0 = lds_f64x2(e);
-            double cr = e0.x * ar[0], ci = e0.x * ai[0];
-#pragma unroll
-            for (int i = 1; i < M; ++i) {
-                const double2 ev = lds_f64x2(e + 16 * i);
-                cr = fma(ev.x, ar[i], fma(ev.y, ai[i], cr));
-                ci = fma(ev.x, ai[i], fma(-ev.y, ar[i], ci));
-            }
-            d[b] = fma(-cr, cr, fma(-ci, ci, na));
-            // screen on the high words (ALU pipe): negative d and anything within one high-word
-            // step of the guard go to the exact test below
-            slow |= (__double2hiint(d[b]) <= hg);
+        for (int b = 0; b < SCAN_WPT; ++b) {
+            const double d = complement_denominator<M>(ar, ai, na, sVg + 8 * (b * vsz + 2 * (M - 1) * M));
+            const int hds = __double2hiint(d);
+            const unsigned hd = (unsigned)hds;
+            const bool guard = hds <= hg;
+            if ((hd - hbm1[b]) <= 1u || guard) cold |= 1u << b;
+            if (hd < hbm1[b] && !guard) { bestd[b] = d; bestk[b] = k; hbm1[b] = max(hd, 1u) - 1u; }
         }
-        if (slow) {
+        if (cold) {  // rare: exact evaluation, identical to the reference's strict '>' on P = 1/d (:132)
 #pragma unroll
-            for (int b = 0; b < SCAN_B; ++b)
-                if (d[b] < gna) d[b] = direct_denominator<M>(ar, ai, sV0 + 8 * b * vsz);
-        }
-        // Running minimum.  Screen on the high 32 bits (sign, exponent, top 20 mantissa bits;
-        // unsigned, so NaNs and negative-signed values sort last): hd < hi(best) - 1 means d is below
-        // the minimum by at least 2^-20 relative - accept.  hd in {hi(best)-1, hi(best)} is ambiguous
-        // (includes exact ties) and is settled exactly, once per tile, in the cold block.
-        bool amb = false;
-#pragma unroll
-        for (int b = 0; b < SCAN_B; ++b) {
-            const unsigned hd = (unsigned)__double2hiint(d[b]);
-            amb |= (hd - hbm1[b]) <= 1u;
-            if (hd < hbm1[b]) { bestd[b] = d[b]; bestk[b] = k; hbm1[b] = max(hd, 1u) - 1u; }
-        }
-        if (amb) {
-#pragma unroll
-            for (int b = 0; b < SCAN_B; ++b) {
-                if (d[b] < bestd[b]) {  // exactly the reference's rule: replace iff 1/d > 1/best (:132)
-                    if (d[b] < bestd[b] * 0.99999999999999911182 /* 1 - 2^-50 */ || 1.0 / d[b] > 1.0 / bestd[b]) {
-                        bestd[b] = d[b];
-                        bestk[b] = k;
-                        hbm1[b] = max((unsigned)__double2hiint(d[b]), 1u) - 1u;
+            for (int b = 0; b < SCAN_WPT; ++b) {
+                if (cold & (1u << b)) {
+                    double d = complement_denominator<M>(ar, ai, na, sVg + 8 * (b * vsz + 2 * (M - 1) * M));
+                    if (d < gna) d = direct_denominator<M>(ar, ai, sVg + 8 * b * vsz);
+                    if (d < bestd[b]) {
+                        if (d < bestd[b] * 0.99999999999999911182 /* 1 - 2^-50 */ || 1.0 / d > 1.0 / bestd[b]) {
+                            bestd[b] = d;
+                            bestk[b] = k;
+                            hbm1[b] = max((unsigned)__double2hiint(d), 1u) - 1u;
+                        }
                     }
                 }
             }
         }
     }
-    __shared__ double rP[SCAN_B][TILE / 32];
-    __shared__ int rk[SCAN_B][TILE / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // per-window merge over the SCAN_BINS threads of the group, order (P desc, bin asc)
+    constexpr int WPG = SCAN_BINS / 32;  // warps per group
+    __shared__ double rP[SCAN_B][WPG];
+    __shared__ int rk[SCAN_B][WPG];
+    const int lane = threadIdx.x & 31, wig = (threadIdx.x >> 5) % WPG;
 #pragma unroll
-    for (int b = 0; b < SCAN_B; ++b) {
+    for (int b = 0; b < SCAN_WPT; ++b) {
         int kk = bestk[b];
         double P = kk >= 0 ? 1.0 / bestd[b] : 0.0;
 #pragma unroll
@@ -823,14 +832,14 @@ __global__ void __launch_bounds__(TILE) scan_peak1_kernel(const double *__restri
             const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
             if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
         }
-        if (lane == 0) { rP[b][wid] = P; rk[b][wid] = kk; }
+        if (lane == 0) { rP[g * SCAN_WPT + b][wig] = P; rk[g * SCAN_WPT + b][wig] = kk; }
     }
     __syncthreads();
     if (threadIdx.x < nb) {
         const int b = threadIdx.x;
         double P = rP[b][0];
         int kk = rk[b][0];
-        for (int q = 1; q < TILE / 32; ++q)
+        for (int q = 1; q < WPG; ++q)
             if (peak_better(rP[b][q], rk[b][q], P, kk)) { P = rP[b][q]; kk = rk[b][q]; }
         const size_t o = (size_t)(w0 + b);
         if (kk >= 0) {
