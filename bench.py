@@ -309,34 +309,54 @@ def run_ours(args):
     roof = None
     stages = None
     if rank == 0:
-        blk.set_stage_timing(True)
-        reps = 5
-        for _ in range(reps):
-            blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(),
-                               stream=stream.cuda_stream)
-        torch.cuda.synchronize()
-        ms4, chunks = blk.stage_times_ms()
-        blk.set_stage_timing(False)
-        cov_ms = ms4[0] / reps
-        stages = {"cov_ms": cov_ms, "eig_ms": ms4[1] / reps, "scan_ms": ms4[2] / reps, "topn_ms": ms4[3] / reps,
-                  "launches_per_step": chunks // reps}
+        def time_stages(b, reps=5):
+            b.set_stage_timing(True)
+            for _ in range(reps):
+                b.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(),
+                                 stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            ms4, chunks = b.stage_times_ms()
+            b.set_stage_timing(False)
+            return [m / reps for m in ms4], chunks // reps
+
+        ms4, _ = time_stages(blk)
+        fused = cfg["m"] == 4 and n == 1 and os.environ.get("MUSIC_B200_FUSED", "1") != "0"
+        dom_ms = ms4[0]  # fused: the single K1+K2+K3 kernel; otherwise K1 covariance
+        kernel = "music4_fused_kernel (K1 covariance + K2 eig + K3 scan in one persistent launch)" if fused \
+            else "K1 covariance (cov4_tma_kernel / cov_tile_kernel)"
+        # the three stages timed separately on a second handle that runs the unfused kernels
+        old_env = os.environ.get("MUSIC_B200_FUSED")
+        os.environ["MUSIC_B200_FUSED"] = "0"
+        blk3 = music_doa(cfg["m"], n, cfg["nsamples"], resp, K, device=local)
+        if old_env is None:
+            del os.environ["MUSIC_B200_FUSED"]
+        else:
+            os.environ["MUSIC_B200_FUSED"] = old_env
+        for _ in range(2):
+            blk3.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(),
+                                stream=stream.cuda_stream)
+        s4, nl = time_stages(blk3)
+        blk3.close()
+        stages = {"unfused_cov_ms": s4[0], "unfused_eig_ms": s4[1], "unfused_scan_ms": s4[2], "unfused_topn_ms": s4[3],
+                  "default_path_kernel_ms": dom_ms, "default_path": "fused" if fused else "three kernels"}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = bytes_per_window(cfg) * W / (cov_ms * 1e-3) / 1e9
+        achieved = bytes_per_window(cfg) * W / (dom_ms * 1e-3) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("config%d" % args.config)
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "K1 covariance (cov_tile_kernel)", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy), of measured" if peaks else "fallback 6650 GB/s, of fallback",
                 "traffic": traffic, "bytes_per_window": bytes_per_window(cfg), "windows_per_launch": W,
-                "whole_step_frac": (bytes_per_window(cfg) * value / G / 1e9) / peak}
+                "whole_step_frac": (bytes_per_window(cfg) * value / G / 1e9) / peak,
+                "unfused_cov_kernel_frac": bytes_per_window(cfg) * W / (s4[0] * 1e-3) / 1e9 / peak}
 
     # ---- e2e: block API with pinned host buffers (H2D + D2H inside the timed region) --------
     e2e = None

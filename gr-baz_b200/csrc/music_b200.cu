@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "music_kernels.cuh"
+#include "music_fused.cuh"
 
 using namespace music;
 
@@ -59,6 +60,7 @@ struct music_b200 {
     cudaStream_t s_cov = nullptr, s_scan = nullptr;
     cudaEvent_t ev_in = nullptr;
     bool pipeline = false;   // MUSIC_B200_PIPE=1 enables the sub-batch pipeline (launch-bound at 10k windows: off)
+    bool fused = true;       // MUSIC_B200_FUSED=0 forces the three-kernel path
     bool scan_fast = true;   // MUSIC_B200_SCAN=general disables the specialised n == 1 kernel
     int cov_tma_stages = 6;  // 0 = LDG tile kernel (MUSIC_B200_COV=ldg), 4 or 6 = TMA ring depth
     // optional per-stage timing (bench.py's roofline leg): events around K1/K2/K3/top-n per chunk
@@ -102,13 +104,16 @@ int fail(music_b200 *h, int code, const char *fmt, ...)
                         "%s failed: %s", #expr, cudaGetErrorString(e_));                        \
     } while (0)
 
-size_t soa_doubles(uint32_t K, uint32_t M) { return (size_t)((K + TILE - 1) / TILE) * (2 * M + 1) * TILE; }
+// Table rows are padded (||a||^2 = +inf) to whole TILE-row tiles covering both K and the rows the
+// fused kernel's 224-thread scan touches.
+uint32_t table_tiles(uint32_t K) { return (uint32_t)((std::max<int>((int)K, fused_scan_rows((int)K)) + TILE - 1) / TILE); }
+size_t soa_doubles(uint32_t K, uint32_t M) { return (size_t)table_tiles(K) * (2 * M + 1) * TILE; }
 
 int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t st)
 {
     DeviceTable &t = h->table[slot];
     CU(h, cudaMemcpyAsync(t.c64, table_c64, (size_t)h->K * h->m * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-    const int ntiles = (h->K + TILE - 1) / TILE;
+    const int ntiles = (int)table_tiles(h->K);
     prep_table_kernel<<<ntiles, TILE, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.soa, (int)h->K, (int)h->m);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -282,6 +287,18 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
     if (nwindows == 0) return MUSIC_B200_OK;
     if (!d_in || !d_ang) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 and d_angles must not be NULL");
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 must be 16-byte aligned");
+    if (h->fused && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
+        // whole call in one persistent launch (music_fused.cuh); no workspace involved
+        cudaEvent_t *tev = timing_events(h);
+        if (tev) cudaEventRecord(tev[0], st);
+        const int grid = std::min<int>(h->sm_count, (int)((nwindows + FZ_COV_WARPS - 1) / FZ_COV_WARPS));
+        music4_fused_kernel<<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, h->table[h->cur_table].soa, (int)nwindows, (int)h->N,
+                                                             (int)h->K, PeakOut{d_ang, d_lvl, d_bins});
+        h->launches++;
+        if (tev) for (int i = 1; i < 5; ++i) cudaEventRecord(tev[i], st);
+        CU(h, cudaGetLastError());
+        return MUSIC_B200_OK;
+    }
     const bool internal_p64 = (h->n != 1) && !d_P64;
     const uint32_t max_sub = max_sub_windows(h, internal_p64);
     const bool pipe = allow_pipeline && h->pipeline && !h->timing && nwindows >= 2 * MIN_SUB;
@@ -454,6 +471,8 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
             else if (!strcmp(e, "tma6")) h->cov_tma_stages = 6;
         }
         if (const char *e = getenv("MUSIC_B200_SCAN")) h->scan_fast = strcmp(e, "general") != 0;
+        if (const char *e = getenv("MUSIC_B200_FUSED")) h->fused = atoi(e) != 0;
+        CU(h, cudaFuncSetAttribute(music4_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 6 * COV_CHUNK));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 4 * COV_CHUNK));
         return upload_table(h, 0, table_c64, h->streams[0]);

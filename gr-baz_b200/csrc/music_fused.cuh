@@ -1,0 +1,304 @@
+// music_fused.cuh - FUSED persistent kernel for the headline shape class (M = 4, n = 1, peak
+// outputs only): K1 + K2 + K3 in one launch, one CTA per SM, warp-specialised; R and the
+// eigenvectors never leave shared memory.
+//
+//   warps 0..7   covariance: per-warp TMA ring exactly as cov4_tma_kernel; a finished window's R
+//                is pushed into a 64-slot shared-memory queue (in-order publish).
+//   warp  8      eigensolver: one lane per queued window (up to 32 at once), cyclic Jacobi
+//                (herm_eig_body<4>), eigenvectors written next to the queue slot.
+//   warps 9..15  pseudospectrum scan + peak pick of up to 4 windows per pass: thread <-> bin,
+//                same hot loop as scan_peak1_kernel, results merged over the 7 warps and written
+//                to global (angle, level, bin).
+//
+// The stages overlap in time on every SM: while the covariance warps keep HBM busy (their FP64
+// demand is ~1/3 of the pipe), the scan warps fill the remaining FP64 issue slots.  Counters in
+// shared memory (cov_pub >= eig_done >= scan_done) hand windows from stage to stage.
+//
+// Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does
+// per window except the optional spectrum port).
+#pragma once
+#include "music_kernels.cuh"
+
+namespace music {
+
+constexpr int FZ_COV_WARPS = 8;
+constexpr int FZ_SCAN_WARPS = 7;
+constexpr int FZ_THREADS = 32 * (FZ_COV_WARPS + 1 + FZ_SCAN_WARPS);  // 512
+constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224 bins per pass iteration
+constexpr int FZ_Q = 64;        // window queue slots per CTA
+constexpr int FZ_WPT = 4;       // windows per scan pass
+constexpr int FZ_STAGES = 5;    // 4 KiB TMA stages per covariance warp
+
+struct FusedCtl {               // shared-memory control block
+    unsigned cov_seq;           // tickets handed to covariance warps
+    volatile unsigned cov_pub;  // windows whose R is in the queue
+    volatile unsigned eig_done; // windows whose eigenvectors are in the queue
+    volatile unsigned scan_done;// windows fully processed (queue slot free)
+    volatile unsigned cov_finished;  // covariance warps that ran out of windows
+    volatile unsigned batch_start, batch_cnt;
+    unsigned pad;
+};
+
+constexpr size_t FZ_OFF_CTL = 1024;
+constexpr size_t FZ_OFF_WIN = 1088;                           // int win[FZ_Q]
+constexpr size_t FZ_OFF_RED = FZ_OFF_WIN + 4 * FZ_Q;          // reduction scratch: 7 warps x 4 x (double, int)
+constexpr size_t FZ_OFF_RQ = 2048;                            // double Rq[FZ_Q][32]
+constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
+constexpr size_t FZ_OFF_RING = FZ_OFF_VQ + (size_t)FZ_Q * 256;
+constexpr size_t FZ_SMEM = FZ_OFF_RING + (size_t)FZ_COV_WARPS * FZ_STAGES * COV_CHUNK;
+static_assert(FZ_OFF_RED + 12 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_RQ, "control area overflow");
+
+__device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_SCAN_THREADS) : "memory"); }
+
+// Bins covered by the scan warps per window: niter * 224; the steering table must be padded to at
+// least that many rows (prep_table_kernel pads whole TILE-row tiles with ||a||^2 = +inf).
+__host__ __device__ inline int fused_scan_rows(int K) { return (K + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS * FZ_SCAN_THREADS; }
+
+__global__ void __launch_bounds__(FZ_THREADS, 1)
+music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa, int W, int N, int K, PeakOut out)
+{
+    extern __shared__ __align__(128) unsigned char fz_smem[];
+    FusedCtl *ctl = reinterpret_cast<FusedCtl *>(fz_smem + FZ_OFF_CTL);
+    int *qwin = reinterpret_cast<int *>(fz_smem + FZ_OFF_WIN);
+    double *Rq = reinterpret_cast<double *>(fz_smem + FZ_OFF_RQ);
+    double *Vq = reinterpret_cast<double *>(fz_smem + FZ_OFF_VQ);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        ctl->cov_seq = 0; ctl->cov_pub = 0; ctl->eig_done = 0; ctl->scan_done = 0; ctl->cov_finished = 0;
+        ctl->batch_start = 0; ctl->batch_cnt = 0;
+    }
+    __syncthreads();
+
+    if (warp < FZ_COV_WARPS) {
+        // ================= covariance warps =================
+        uint64_t *bars = reinterpret_cast<uint64_t *>(fz_smem) + warp * FZ_STAGES;
+        unsigned char *ring = fz_smem + FZ_OFF_RING + (size_t)warp * FZ_STAGES * COV_CHUNK;
+        const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
+        const int gw = blockIdx.x * FZ_COV_WARPS + warp, total_warps = gridDim.x * FZ_COV_WARPS;
+        const size_t win_bytes = (size_t)N * 32;
+        const int cpw = (int)((win_bytes + COV_CHUNK - 1) / COV_CHUNK);
+        const int nwin = gw < W ? (W - gw + total_warps - 1) / total_warps : 0;
+        const long long total = (long long)nwin * cpw;
+        const unsigned char *src0 = reinterpret_cast<const unsigned char *>(in);
+        if (lane == 0) {
+            for (int s = 0; s < FZ_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        auto issue = [&](long long c) {  // lane 0 only
+            const int j = (int)(c / cpw), q = (int)(c % cpw);
+            const size_t off = (size_t)q * COV_CHUNK;
+            const uint32_t bytes = (uint32_t)min((size_t)COV_CHUNK, win_bytes - off);
+            const int slot = (int)(c % FZ_STAGES);
+            const unsigned char *src = src0 + ((size_t)gw + (size_t)j * total_warps) * win_bytes + off;
+            mbar_expect_tx(bar0 + 8 * slot, bytes);
+            bulk_g2s(ring0 + slot * COV_CHUNK, src, bytes, bar0 + 8 * slot);
+        };
+        if (lane == 0)
+            for (long long c = 0; c < total && c < FZ_STAGES; ++c) issue(c);
+        double acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+        int q = 0, j = 0, slot = 0;
+        uint32_t parity = 0;
+        for (long long c = 0; c < total; ++c) {
+            while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
+            const size_t off = (size_t)q * COV_CHUNK;
+            const int nsnap = (int)(min((size_t)COV_CHUNK, win_bytes - off) >> 5);
+            const float4 *buf = reinterpret_cast<const float4 *>(ring + (size_t)slot * COV_CHUNK);
+            if (nsnap == COV_CHUNK / 32) {
+                float4 xa[4], xb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    xa[u] = buf[2 * (lane + 32 * u)];
+                    xb[u] = buf[2 * (lane + 32 * u) + 1];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cov4_accumulate(acc, xa[u], xb[u]);
+            } else {
+                for (int s = lane; s < nsnap; s += 32) cov4_accumulate(acc, buf[2 * s], buf[2 * s + 1]);
+            }
+            __syncwarp();
+            if (lane == 0 && c + FZ_STAGES < total) issue(c + FZ_STAGES);
+            if (++slot == FZ_STAGES) { slot = 0; parity ^= 1; }
+            if (++q == cpw) {
+                q = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+                if (lane == 0) {
+                    const unsigned seq = atomicAdd(&ctl->cov_seq, 1u);
+                    while (seq - ctl->scan_done >= (unsigned)FZ_Q) __nanosleep(100);  // queue slot free?
+                    const double dn = (double)N;
+                    double *Rw = Rq + (size_t)(seq % FZ_Q) * 32;
+                    Rw[0] = acc[0] / dn;   Rw[1] = 0.0;
+                    Rw[10] = acc[1] / dn;  Rw[11] = 0.0;
+                    Rw[20] = acc[2] / dn;  Rw[21] = 0.0;
+                    Rw[30] = acc[3] / dn;  Rw[31] = 0.0;
+                    int e = 4;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = a + 1; b < 4; ++b) {
+                            const double re = acc[e] / dn, im = acc[e + 1] / dn;
+                            Rw[2 * (a * 4 + b)] = re;  Rw[2 * (a * 4 + b) + 1] = im;
+                            Rw[2 * (b * 4 + a)] = re;  Rw[2 * (b * 4 + a) + 1] = -im;
+                            e += 2;
+                        }
+                    qwin[seq % FZ_Q] = gw + j * total_warps;
+                    while (ctl->cov_pub != seq) {}  // publish in ticket order
+                    __threadfence_block();
+                    ctl->cov_pub = seq + 1;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+                ++j;
+            }
+        }
+        if (lane == 0) atomicAdd((unsigned *)&ctl->cov_finished, 1u);
+    } else if (warp == FZ_COV_WARPS) {
+        // ================= eigensolver warp =================
+        for (;;) {
+            const unsigned done = ctl->eig_done;
+            const unsigned avail = ctl->cov_pub - done;
+            if (avail == 0) {
+                if (ctl->cov_finished == (unsigned)FZ_COV_WARPS && ctl->cov_pub == done) break;
+                __nanosleep(200);
+                continue;
+            }
+            __threadfence_block();
+            const unsigned cnt = min(avail, 32u);
+            if ((unsigned)lane < cnt) {
+                const unsigned slot = (done + lane) % FZ_Q;
+                herm_eig_body<4, true>(Rq + (size_t)slot * 32, nullptr, Vq + (size_t)slot * 32, 4);
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) ctl->eig_done = done + cnt;
+            __syncwarp();
+        }
+    } else {
+        // ================= scan warps =================
+        constexpr int M = 4, vsz = 32;
+        const int st = threadIdx.x - 32 * (FZ_COV_WARPS + 1);  // 0..223
+        const int swarp = st >> 5;
+        double *redP = reinterpret_cast<double *>(fz_smem + FZ_OFF_RED);  // [7][4]
+        int *redk = reinterpret_cast<int *>(fz_smem + FZ_OFF_RED + 8 * FZ_SCAN_WARPS * FZ_WPT);
+        const uint32_t Vq0 = smem_u32(Vq);
+        const int niter = (K + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS;
+        for (;;) {
+            if (st == 0) {
+                unsigned start, cnt;
+                for (;;) {
+                    start = ctl->scan_done;
+                    const unsigned avail = ctl->eig_done - start;
+                    if (avail > 0) { cnt = min(avail, (unsigned)FZ_WPT); break; }
+                    if (ctl->cov_finished == (unsigned)FZ_COV_WARPS && ctl->cov_pub == start) { cnt = 0; break; }
+                    __nanosleep(200);
+                }
+                ctl->batch_start = start;
+                ctl->batch_cnt = cnt;
+                __threadfence_block();
+            }
+            bar_sync_scan();
+            const unsigned start = ctl->batch_start, cnt = ctl->batch_cnt;
+            if (cnt == 0) break;
+            uint32_t ev[FZ_WPT];  // shared address of each window's eigenvectors (clamped duplicates beyond cnt)
+#pragma unroll
+            for (int b = 0; b < FZ_WPT; ++b) ev[b] = Vq0 + 8 * vsz * ((start + min((unsigned)b, cnt - 1)) % FZ_Q);
+            double bestd[FZ_WPT];
+            unsigned hbm1[FZ_WPT];
+            int bestk[FZ_WPT];
+#pragma unroll
+            for (int b = 0; b < FZ_WPT; ++b) { bestd[b] = __longlong_as_double(0x7ff0000000000000LL); hbm1[b] = 0x7fefffffu; bestk[b] = -1; }
+
+            // table entry of this thread's bin, prefetched one iteration ahead
+            double nar[M], nai[M], nna;
+            {
+                const double *tb = soa + (size_t)(st / TILE) * (2 * M + 1) * TILE + (st % TILE);
+#pragma unroll
+                for (int i = 0; i < M; ++i) { nar[i] = tb[(size_t)(2 * i) * TILE]; nai[i] = tb[(size_t)(2 * i + 1) * TILE]; }
+                nna = tb[(size_t)(2 * M) * TILE];
+            }
+            for (int it = 0; it < niter; ++it) {
+                const int k = it * FZ_SCAN_THREADS + st;
+                double ar[M], ai[M];
+#pragma unroll
+                for (int i = 0; i < M; ++i) { ar[i] = nar[i]; ai[i] = nai[i]; }
+                const double na = nna;
+                if (it + 1 < niter) {
+                    const int kn = k + FZ_SCAN_THREADS;
+                    const double *tb = soa + (size_t)(kn / TILE) * (2 * M + 1) * TILE + (kn % TILE);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) { nar[i] = tb[(size_t)(2 * i) * TILE]; nai[i] = tb[(size_t)(2 * i + 1) * TILE]; }
+                    nna = tb[(size_t)(2 * M) * TILE];
+                }
+                const double gna = COMPLEMENT_GUARD * na;
+                const int hg = __double2hiint(gna);
+                unsigned cold = 0;
+#pragma unroll
+                for (int b = 0; b < FZ_WPT; ++b) {
+                    const double d = complement_denominator<M>(ar, ai, na, ev[b] + 8 * (2 * (M - 1) * M));
+                    const int hds = __double2hiint(d);
+                    const unsigned hd = (unsigned)hds;
+                    const bool guard = hds <= hg;
+                    if ((hd - hbm1[b]) <= 1u || guard) cold |= 1u << b;
+                    if (hd < hbm1[b] && !guard) { bestd[b] = d; bestk[b] = k; hbm1[b] = max(hd, 1u) - 1u; }
+                }
+                if (cold) {
+#pragma unroll
+                    for (int b = 0; b < FZ_WPT; ++b) {
+                        if (cold & (1u << b)) {
+                            double d = complement_denominator<M>(ar, ai, na, ev[b] + 8 * (2 * (M - 1) * M));
+                            if (d < gna) d = direct_denominator<M>(ar, ai, ev[b]);
+                            if (d < bestd[b]) {
+                                if (d < bestd[b] * 0.99999999999999911182 || 1.0 / d > 1.0 / bestd[b]) {
+                                    bestd[b] = d;
+                                    bestk[b] = k;
+                                    hbm1[b] = max((unsigned)__double2hiint(d), 1u) - 1u;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < FZ_WPT; ++b) {
+                int kk = bestk[b];
+                double P = kk >= 0 ? 1.0 / bestd[b] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double Po = __shfl_xor_sync(0xffffffffu, P, o);
+                    const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
+                    if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
+                }
+                if (lane == 0) { redP[swarp * FZ_WPT + b] = P; redk[swarp * FZ_WPT + b] = kk; }
+            }
+            bar_sync_scan();
+            if ((unsigned)st < cnt) {
+                const int b = st;
+                double P = redP[b];
+                int kk = redk[b];
+                for (int q = 1; q < FZ_SCAN_WARPS; ++q)
+                    if (peak_better(redP[q * FZ_WPT + b], redk[q * FZ_WPT + b], P, kk)) { P = redP[q * FZ_WPT + b]; kk = redk[q * FZ_WPT + b]; }
+                const size_t o = (size_t)qwin[(start + b) % FZ_Q];
+                if (kk >= 0) {
+                    out.angles[o] = (float)((double)kk * 360.0 / (double)K);  // reference :134, :153
+                    if (out.levels) out.levels[o] = (float)P;                 // reference :154
+                } else {
+                    out.angles[o] = 0.f;                                      // (0,0) initial pair, reference :95
+                    if (out.levels) out.levels[o] = 0.f;
+                }
+                if (out.bins) out.bins[o] = kk;
+            }
+            bar_sync_scan();  // red[] and the queue slots may be reused from here on
+            if (st == 0) {
+                __threadfence_block();
+                ctl->scan_done = start + cnt;
+            }
+        }
+    }
+}
+
+}  // namespace music

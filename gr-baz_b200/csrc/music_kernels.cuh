@@ -414,15 +414,12 @@ __device__ __forceinline__ void eig_phase(double v0r, double v0i, double &pr, do
 
 // MA = array extent; STATIC: M == MA at compile time, everything unrolled into registers
 // (M = 4); otherwise runtime M <= MA with the matrices in local memory.
+// Rw: M x M complex (row-major, interleaved) in global or shared memory; ew (may be null): M
+// ascending eigenvalues; vw: Vt[j][i], eigenvector j contiguous.
 template <int MA, bool STATIC>
-__global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, double *__restrict__ evals,
-                                                  double *__restrict__ Vt, int Mrt, int W)
+__device__ __forceinline__ void herm_eig_body(const double *Rw, double *ew, double *vw, const int M)
 {
-    const int M = STATIC ? MA : Mrt;
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= W) return;
     double Ar[MA][MA], Ai[MA][MA], Vr[MA][MA], Vi[MA][MA];
-    const double *Rw = R + (size_t)w * M * M * 2;
     if (STATIC) {
 #pragma unroll
         for (int i = 0; i < MA; ++i)
@@ -475,15 +472,13 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
         }
     }
     // ascending, stable: destination slot of column j = #{l : w_l < w_j} + #{l < j : w_l == w_j}
-    double *ew = evals + (size_t)w * M;
-    double *vw = Vt + (size_t)w * M * M * 2;
     if (STATIC) {
 #pragma unroll
         for (int j = 0; j < MA; ++j) {
             int rank = 0;
 #pragma unroll
             for (int l = 0; l < MA; ++l) rank += eig_before(Ar[l][l], l, Ar[j][j], j);
-            ew[rank] = Ar[j][j];
+            if (ew) ew[rank] = Ar[j][j];
             double pr, pi;
             eig_phase(Vr[0][j], Vi[0][j], pr, pi);
 #pragma unroll
@@ -496,7 +491,7 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
         for (int j = 0; j < M; ++j) {
             int rank = 0;
             for (int l = 0; l < M; ++l) rank += eig_before(Ar[l][l], l, Ar[j][j], j);
-            ew[rank] = Ar[j][j];
+            if (ew) ew[rank] = Ar[j][j];
             double pr, pi;
             eig_phase(Vr[0][j], Vi[0][j], pr, pi);
             for (int i = 0; i < M; ++i) {
@@ -505,6 +500,16 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
             }
         }
     }
+}
+
+template <int MA, bool STATIC>
+__global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, double *__restrict__ evals,
+                                                  double *__restrict__ Vt, int Mrt, int W)
+{
+    const int M = STATIC ? MA : Mrt;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    herm_eig_body<MA, STATIC>(R + (size_t)w * M * M * 2, evals + (size_t)w * M, Vt + (size_t)w * M * M * 2, M);
 }
 
 // ------------------------------------------------------------------------------------------

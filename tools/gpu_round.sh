@@ -8,12 +8,12 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu.txt 2>&1
 echo "== smoke" ; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/smoke.log; tail -3 $OUT/smoke.log
 echo "== pytest gpu"; timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log; tail -15 $OUT/pytest_gpu.log
-for var in ${VARIANTS:-"MUSIC_B200_PIPE=0"}; do
+for var in "MUSIC_B200_FUSED=0" "MUSIC_B200_FUSED=1"; do
   tag=$(echo "$var" | tr ' =' '__')
   echo "== bench $var"; env $var timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_$tag.json 2> $OUT/bench_$tag.err; python - <<PY
 import json
 try:
-    d=json.load(open("$OUT/bench_$tag.json")); print("$var", "value=%.3e"%d["value"], "ms/step=%.4f"%d["ms_per_step"], d["stages"], "roof=%.3f whole=%.3f"%(d["roofline"]["frac"], d["roofline"]["whole_step_frac"]), d["clocks"])
+    d=json.load(open("$OUT/bench_$tag.json")); print("$var", "value=%.3e"%d["value"], "ms/step=%.4f"%d["ms_per_step"], {k:(round(v,4) if isinstance(v,float) else v) for k,v in d["stages"].items()}, "roof=%.3f whole=%.3f"%(d["roofline"]["frac"], d["roofline"]["whole_step_frac"]), d["clocks"])
 except Exception as e:
     print("$var FAILED", e); print(open("$OUT/bench_$tag.err").read()[-2000:])
 PY
@@ -23,7 +23,7 @@ if [ "$MODE" = "full" ]; then
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json
 fi
 echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"cov|eig_kernel|scan|topn_kernel|prep_table" -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1; echo "ncu rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"cov|eig_kernel|scan|topn_kernel|prep_table|fused" -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1; echo "ncu rc=$?"
 echo "== ncu full (top kernels)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"cov|scan|eig_kernel" -s 9 -c 3 -o $OUT/prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1; echo "ncu full rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"cov|scan|eig_kernel|fused" -s 9 -c 3 -o $OUT/prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT
