@@ -207,11 +207,8 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
             uint32_t ev[FZ_WPT];  // shared address of each window's eigenvectors (clamped duplicates beyond cnt)
 #pragma unroll
             for (int b = 0; b < FZ_WPT; ++b) ev[b] = Vq0 + 8 * vsz * ((start + min((unsigned)b, cnt - 1)) % FZ_Q);
-            double bestd[FZ_WPT];
-            unsigned hbm1[FZ_WPT];
-            int bestk[FZ_WPT];
-#pragma unroll
-            for (int b = 0; b < FZ_WPT; ++b) { bestd[b] = __longlong_as_double(0x7ff0000000000000LL); hbm1[b] = 0x7fefffffu; bestk[b] = -1; }
+            PeakState<FZ_WPT> ps;
+            ps.reset();
 
             // table entry of this thread's bin, prefetched one iteration ahead
             double nar[M], nai[M], nna;
@@ -234,39 +231,12 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
                     for (int i = 0; i < M; ++i) { nar[i] = tb[(size_t)(2 * i) * TILE]; nai[i] = tb[(size_t)(2 * i + 1) * TILE]; }
                     nna = tb[(size_t)(2 * M) * TILE];
                 }
-                const double gna = COMPLEMENT_GUARD * na;
-                const int hg = __double2hiint(gna);
-                unsigned cold = 0;
-#pragma unroll
-                for (int b = 0; b < FZ_WPT; ++b) {
-                    const double d = complement_denominator<M>(ar, ai, na, ev[b] + 8 * (2 * (M - 1) * M));
-                    const int hds = __double2hiint(d);
-                    const unsigned hd = (unsigned)hds;
-                    const bool guard = hds <= hg;
-                    if ((hd - hbm1[b]) <= 1u || guard) cold |= 1u << b;
-                    if (hd < hbm1[b] && !guard) { bestd[b] = d; bestk[b] = k; hbm1[b] = max(hd, 1u) - 1u; }
-                }
-                if (cold) {
-#pragma unroll
-                    for (int b = 0; b < FZ_WPT; ++b) {
-                        if (cold & (1u << b)) {
-                            double d = complement_denominator<M>(ar, ai, na, ev[b] + 8 * (2 * (M - 1) * M));
-                            if (d < gna) d = direct_denominator<M>(ar, ai, ev[b]);
-                            if (d < bestd[b]) {
-                                if (d < bestd[b] * 0.99999999999999911182 || 1.0 / d > 1.0 / bestd[b]) {
-                                    bestd[b] = d;
-                                    bestk[b] = k;
-                                    hbm1[b] = max((unsigned)__double2hiint(d), 1u) - 1u;
-                                }
-                            }
-                        }
-                    }
-                }
+                scan_bin<M, FZ_WPT>(ar, ai, na, k, ev, ps);
             }
 #pragma unroll
             for (int b = 0; b < FZ_WPT; ++b) {
-                int kk = bestk[b];
-                double P = kk >= 0 ? 1.0 / bestd[b] : 0.0;
+                int kk = ps.bestk[b];
+                double P = kk >= 0 ? 1.0 / ps.bestd[b] : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const double Po = __shfl_xor_sync(0xffffffffu, P, o);

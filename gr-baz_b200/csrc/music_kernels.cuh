@@ -755,6 +755,85 @@ __device__ __forceinline__ double complement_denominator(const double *ar, const
     return fma(-cr, cr, fma(-ci, ci, na));
 }
 
+// Running peak state of WPT windows held by one thread.
+template <int WPT>
+struct PeakState {
+    double bestd[WPT];   // running minimum of d = ||G^H a||^2
+    unsigned hbm1[WPT];  // high word of bestd, minus one (saturating at 0): screening threshold
+    int bestk[WPT];
+    __device__ __forceinline__ void reset()
+    {
+#pragma unroll
+        for (int b = 0; b < WPT; ++b) { bestd[b] = __longlong_as_double(0x7ff0000000000000LL); hbm1[b] = 0x7fefffffu; bestk[b] = -1; }
+    }
+};
+
+// One steering-table row (bin k) against WPT windows.  ev[b]: shared address of window b's sorted
+// eigenvector block (Vt layout).  The loops run antenna-outer / window-inner so that the 2*WPT
+// dot-product chains are independent and interleave in issue order (the DFMA pipe has a long
+// dependent-issue latency; two windows at a time leave it half idle).
+//   hot path : complement form d = ||a||^2 - |e_s^H a|^2, 2 DMUL + 4(M-1)+2 DFMA per window, then a
+//              screen on the high 32 bits of d on the ALU pipe:
+//                hd <= hi(guard)               -> maybe inside the cancellation guard (or negative): cold
+//                hd <  hi(best) - 1 (unsigned) -> below the running minimum by >= 2^-20 relative: accept
+//                hd in {hi(best)-1, hi(best)}  -> ambiguous (includes exact ties): cold
+//              NaNs and negative-signed values are large as unsigned and are never accepted.
+//   cold path: exact evaluation (direct noise-subspace form inside the guard) and the reference's
+//              rule "replace iff 1/d > 1/best" (strict '>' on the strengths, :132).
+template <int M, int WPT>
+__device__ __forceinline__ void scan_bin(const double (&ar)[M], const double (&ai)[M], const double na, const int k,
+                                         const uint32_t (&ev)[WPT], PeakState<WPT> &ps)
+{
+    constexpr int sig = 16 * (M - 1) * M;  // byte offset of the signal vector (largest eigenvalue)
+    double cr[WPT], ci[WPT];
+#pragma unroll
+    for (int b = 0; b < WPT; ++b) {
+        double e0x;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(e0x) : "r"(ev[b] + sig));
+        cr[b] = e0x * ar[0];
+        ci[b] = e0x * ai[0];
+    }
+#pragma unroll
+    for (int i = 1; i < M; ++i) {
+#pragma unroll
+        for (int b = 0; b < WPT; ++b) {
+            const double2 e = lds_f64x2(ev[b] + sig + 16 * i);
+            cr[b] = fma(e.x, ar[i], cr[b]);
+            ci[b] = fma(e.x, ai[i], ci[b]);
+            cr[b] = fma(e.y, ai[i], cr[b]);
+            ci[b] = fma(-e.y, ar[i], ci[b]);
+        }
+    }
+    const double gna = COMPLEMENT_GUARD * na;
+    const int hg = __double2hiint(gna);
+    unsigned cold = 0;
+#pragma unroll
+    for (int b = 0; b < WPT; ++b) {
+        const double d = fma(-cr[b], cr[b], fma(-ci[b], ci[b], na));
+        const int hds = __double2hiint(d);
+        const unsigned hd = (unsigned)hds;
+        const bool guard = hds <= hg;
+        if ((hd - ps.hbm1[b]) <= 1u || guard) cold |= 1u << b;
+        if (hd < ps.hbm1[b] && !guard) { ps.bestd[b] = d; ps.bestk[b] = k; ps.hbm1[b] = max(hd, 1u) - 1u; }
+    }
+    if (cold) {
+#pragma unroll
+        for (int b = 0; b < WPT; ++b) {
+            if (cold & (1u << b)) {
+                double d = complement_denominator<M>(ar, ai, na, ev[b] + sig);
+                if (d < gna) d = direct_denominator<M>(ar, ai, ev[b]);
+                if (d < ps.bestd[b]) {
+                    if (d < ps.bestd[b] * 0.99999999999999911182 /* 1 - 2^-50 */ || 1.0 / d > 1.0 / ps.bestd[b]) {
+                        ps.bestd[b] = d;
+                        ps.bestk[b] = k;
+                        ps.hbm1[b] = max((unsigned)__double2hiint(d), 1u) - 1u;
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int M>
 __global__ void __launch_bounds__(TILE, 3) scan_peak1_kernel(const double *__restrict__ soa, const double *__restrict__ Vt,
                                                              int K, int W, PeakOut out)
@@ -770,12 +849,11 @@ __global__ void __launch_bounds__(TILE, 3) scan_peak1_kernel(const double *__res
     __syncthreads();
 
     const int g = threadIdx.x / SCAN_BINS, t = threadIdx.x % SCAN_BINS;
-    const uint32_t sVg = smem_u32(sV) + 8 * (g * SCAN_WPT * vsz);  // this thread's first window
-    double bestd[SCAN_WPT];     // running minimum of d
-    unsigned hbm1[SCAN_WPT];    // high word of bestd, minus one (saturating at 0): screening threshold
-    int bestk[SCAN_WPT];
+    uint32_t ev[SCAN_WPT];
 #pragma unroll
-    for (int b = 0; b < SCAN_WPT; ++b) { bestd[b] = __longlong_as_double(0x7ff0000000000000LL); hbm1[b] = 0x7fefffffu; bestk[b] = -1; }
+    for (int b = 0; b < SCAN_WPT; ++b) ev[b] = smem_u32(sV) + 8 * ((g * SCAN_WPT + b) * vsz);
+    PeakState<SCAN_WPT> ps;
+    ps.reset();
 
     const int niter = (K + SCAN_BINS - 1) / SCAN_BINS;
     for (int it = 0; it < niter; ++it) {
@@ -788,39 +866,7 @@ __global__ void __launch_bounds__(TILE, 3) scan_peak1_kernel(const double *__res
             ai[i] = tb[(size_t)(2 * i + 1) * TILE];
         }
         const double na = tb[(size_t)(2 * M) * TILE];
-        const double gna = COMPLEMENT_GUARD * na;
-        const int hg = __double2hiint(gna);
-        // Hot loop: d by the complement form, then a screen on the high 32 bits of d (ALU pipe):
-        //   hd <= hi(guard)              -> maybe inside the cancellation guard (or negative): cold
-        //   hd <  hi(best) - 1 (unsigned) -> below the running minimum by >= 2^-20 relative: accept
-        //   hd in {hi(best)-1, hi(best)}  -> ambiguous (includes exact ties): cold
-        // NaNs and negative-signed values are large as unsigned and are never accepted.
-        unsigned cold = 0;
-#pragma unroll
-        for (int b = 0; b < SCAN_WPT; ++b) {
-            const double d = complement_denominator<M>(ar, ai, na, sVg + 8 * (b * vsz + 2 * (M - 1) * M));
-            const int hds = __double2hiint(d);
-            const unsigned hd = (unsigned)hds;
-            const bool guard = hds <= hg;
-            if ((hd - hbm1[b]) <= 1u || guard) cold |= 1u << b;
-            if (hd < hbm1[b] && !guard) { bestd[b] = d; bestk[b] = k; hbm1[b] = max(hd, 1u) - 1u; }
-        }
-        if (cold) {  // rare: exact evaluation, identical to the reference's strict '>' on P = 1/d (:132)
-#pragma unroll
-            for (int b = 0; b < SCAN_WPT; ++b) {
-                if (cold & (1u << b)) {
-                    double d = complement_denominator<M>(ar, ai, na, sVg + 8 * (b * vsz + 2 * (M - 1) * M));
-                    if (d < gna) d = direct_denominator<M>(ar, ai, sVg + 8 * b * vsz);
-                    if (d < bestd[b]) {
-                        if (d < bestd[b] * 0.99999999999999911182 /* 1 - 2^-50 */ || 1.0 / d > 1.0 / bestd[b]) {
-                            bestd[b] = d;
-                            bestk[b] = k;
-                            hbm1[b] = max((unsigned)__double2hiint(d), 1u) - 1u;
-                        }
-                    }
-                }
-            }
-        }
+        scan_bin<M, SCAN_WPT>(ar, ai, na, k, ev, ps);
     }
     // per-window merge over the SCAN_BINS threads of the group, order (P desc, bin asc)
     constexpr int WPG = SCAN_BINS / 32;  // warps per group
@@ -829,8 +875,8 @@ __global__ void __launch_bounds__(TILE, 3) scan_peak1_kernel(const double *__res
     const int lane = threadIdx.x & 31, wig = (threadIdx.x >> 5) % WPG;
 #pragma unroll
     for (int b = 0; b < SCAN_WPT; ++b) {
-        int kk = bestk[b];
-        double P = kk >= 0 ? 1.0 / bestd[b] : 0.0;
+        int kk = ps.bestk[b];
+        double P = kk >= 0 ? 1.0 / ps.bestd[b] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double Po = __shfl_xor_sync(0xffffffffu, P, o);

@@ -24,6 +24,8 @@ echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 
 fi
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"cov|eig_kernel|scan|topn_kernel|prep_table|fused" -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1; echo "ncu rc=$?"
-echo "== ncu full (top kernels)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"cov|scan|eig_kernel|fused" -s 9 -c 3 -o $OUT/prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1; echo "ncu full rc=$?"
+echo "== ncu full (fused kernel, then the three unfused kernels)"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"fused" -s 3 -c 1 -o $OUT/prof_fused python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_full_fused.log 2>&1; echo "ncu fused rc=$?"
+MUSIC_B200_FUSED=0 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"cov|scan|eig_kernel" -s 9 -c 3 -o $OUT/prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1; echo "ncu full rc=$?"
+if [ -x tools/microbench ]; then (cd tools && timeout 300 ./microbench) > $OUT/microbench.log 2>&1; head -8 $OUT/microbench.log; fi
 ls -la $OUT

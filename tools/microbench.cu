@@ -25,6 +25,27 @@ __global__ void k_dfma(double *out, double a, double b, long long *cyc)
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+template <int CH>
+__global__ void k_dfma_chains(double *out, double a, double b, long long *cyc)
+{
+    double acc[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) acc[i] = threadIdx.x + i;
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8 / CH; ++r)
+#pragma unroll
+            for (int i = 0; i < CH; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    long long t1 = clock64();
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 __global__ void k_f2f(double *out, int seed, long long *cyc)
 {
     int v[8];
@@ -159,7 +180,12 @@ int main()
     double *out; long long *cyc;
     cudaMalloc(&out, sizeof(double) * sms * 8 * 1024);
     cudaMalloc(&cyc, sizeof(long long) * sms * 8);
-    for (int tpb : {128, 256, 512, 1024}) {
+    // dependent-issue latency of DFMA: one warp per SMSP, CH independent chains -> lane-ops/clk/SM = 128*CH/L... (L = 4*32*CH/rate)
+    run("DFMA 1 chain, 1 warp/SMSP", [&](int g, int t) { k_dfma_chains<1><<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, 128, 1, sms, cyc);
+    run("DFMA 2 chains, 1 warp/SMSP", [&](int g, int t) { k_dfma_chains<2><<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, 128, 1, sms, cyc);
+    run("DFMA 4 chains, 1 warp/SMSP", [&](int g, int t) { k_dfma_chains<4><<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, 128, 1, sms, cyc);
+    run("DFMA 8 chains, 1 warp/SMSP", [&](int g, int t) { k_dfma_chains<8><<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, 128, 1, sms, cyc);
+    for (int tpb : {128, 1024}) {
         run("DFMA", [&](int g, int t) { k_dfma<<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, tpb, 1, sms, cyc);
         run("F2F.F64.F32", [&](int g, int t) { k_f2f<<<g, t>>>(out, 1, cyc); }, 8, tpb, 1, sms, cyc);
         run("DFMA:F2F 4:1 (count DFMA)", [&](int g, int t) { k_mix<4><<<g, t>>>(out, 1, 1e-9, cyc); }, 8, tpb, 1, sms, cyc);
