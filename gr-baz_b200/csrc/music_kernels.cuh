@@ -402,6 +402,55 @@ __device__ __forceinline__ bool eig_before(double wl, int l, double wj, int j)
     return (wl < wj) || (wl == wj && l < j);
 }
 
+// Branch-free variant for the fully unrolled M = 4 solver: no early-out, reciprocal square roots
+// instead of sqrt + divide (3 rsqrt + 1 reciprocal per rotation), so that the two disjoint
+// rotations of a parallel-ordering step are one basic block and their dependent chains
+// interleave.  The eigensolver is latency-bound (one lane per window), and in the fused kernel
+// its latency is the pipeline's tail.
+template <int MA>
+__device__ __forceinline__ void jacobi_rotate_bf(double (&Ar)[MA][MA], double (&Ai)[MA][MA], double (&Vr)[MA][MA],
+                                                 double (&Vi)[MA][MA], const int p, const int q)
+{
+    const double gr = Ar[p][q], gi = Ai[p][q];
+    const double gg = fma(gr, gr, gi * gi);
+    const bool nz = gg > 0.0;                      // false for 0 and NaN (NaN then propagates via g)
+    const double rg = nz ? rsqrt(gg) : 0.0;        // 1 / |a_pq|
+    const double g = (gg != gg) ? gg : gg * rg;    // |a_pq| (NaN stays NaN)
+    const double app = Ar[p][p], aqq = Ar[q][q];
+    const double er = gr * rg, ei = gi * rg;
+    double theta = 0.5 * (aqq - app) * rg;
+    theta = fmin(fmax(theta, -1e150), 1e150);      // keeps theta^2 finite; |t| ~ 1/(2|theta|) ~ 0 there
+    const double q1 = fma(theta, theta, 1.0);
+    const double sq = q1 * rsqrt(q1);              // sqrt(theta^2 + 1)
+    double t = 1.0 / (fabs(theta) + sq);
+    t = nz ? copysign(t, theta) : 0.0;
+    const double c = rsqrt(fma(t, t, 1.0));
+    const double s = t * c;
+    const double swr = s * er, swi = s * ei;       // s * e,  e = a_pq / |a_pq|
+#pragma unroll
+    for (int k = 0; k < MA; ++k) {
+        if (k == p || k == q) continue;
+        const double kpr = Ar[k][p], kpi = Ai[k][p], kqr = Ar[k][q], kqi = Ai[k][q];
+        const double npr = c * kpr - (swr * kqr + swi * kqi);
+        const double npi = c * kpi - (swr * kqi - swi * kqr);
+        const double nqr = c * kqr + (swr * kpr - swi * kpi);
+        const double nqi = c * kqi + (swr * kpi + swi * kpr);
+        Ar[k][p] = npr; Ai[k][p] = npi; Ar[k][q] = nqr; Ai[k][q] = nqi;
+        Ar[p][k] = npr; Ai[p][k] = -npi; Ar[q][k] = nqr; Ai[q][k] = -nqi;
+    }
+    Ar[p][p] = app - t * g; Ai[p][p] = 0.0;
+    Ar[q][q] = aqq + t * g; Ai[q][q] = 0.0;
+    Ar[p][q] = 0.0; Ai[p][q] = 0.0; Ar[q][p] = 0.0; Ai[q][p] = 0.0;
+#pragma unroll
+    for (int k = 0; k < MA; ++k) {
+        const double kpr = Vr[k][p], kpi = Vi[k][p], kqr = Vr[k][q], kqi = Vi[k][q];
+        Vr[k][p] = c * kpr - (swr * kqr + swi * kqi);
+        Vi[k][p] = c * kpi - (swr * kqi - swi * kqr);
+        Vr[k][q] = c * kqr + (swr * kpr - swi * kpi);
+        Vi[k][q] = c * kqi + (swr * kpi + swi * kpr);
+    }
+}
+
 // Unit phasor p = conj(v0)/|v0| that makes component 0 of an eigenvector real and >= 0 (any
 // phase is a valid eigenvector; MUSIC only uses |e^H a| and the projector).  The scan kernels
 // rely on Im(v0) == 0 to drop two multiply-adds per bin.
@@ -459,7 +508,12 @@ __device__ __forceinline__ void herm_eig_body(const double *Rw, double *ew, doub
                 }
         }
         if (off <= 1e-32 * fro || off == 0.0) break;
-        if (STATIC) {
+        if (STATIC && MA == 4) {
+            // parallel (round-robin) ordering: the two rotations of a step touch disjoint rows/columns
+            jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 0, 1); jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 2, 3);
+            jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 0, 2); jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 1, 3);
+            jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 0, 3); jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 1, 2);
+        } else if (STATIC) {
 #pragma unroll
             for (int p = 0; p < MA - 1; ++p)
 #pragma unroll
