@@ -55,6 +55,8 @@ def load():
         L.music_b200_set_stage_timing.restype = ctypes.c_int
         L.music_b200_get_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
         L.music_b200_get_stage_times.restype = ctypes.c_int
+        L.music_b200_debug_fused_trace.argtypes = [vp, ctypes.c_void_p, ctypes.c_int]
+        L.music_b200_debug_fused_trace.restype = ctypes.c_int
         L.music_b200_last_error.argtypes = [vp]
         L.music_b200_last_error.restype = ctypes.c_char_p
         L.music_b200_destroy.argtypes = [vp]
@@ -66,7 +68,7 @@ def load():
 EXPORTS = [
     "music_b200_version", "music_b200_create", "music_b200_set_table", "music_b200_process_host",
     "music_b200_process_device", "music_b200_process_device_ex", "music_b200_launch_count",
-    "music_b200_set_stage_timing", "music_b200_get_stage_times",
+    "music_b200_set_stage_timing", "music_b200_get_stage_times", "music_b200_debug_fused_trace",
     "music_b200_last_error", "music_b200_destroy",
 ]
 

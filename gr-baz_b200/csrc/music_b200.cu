@@ -32,6 +32,7 @@ std::string g_create_error;
 struct DeviceTable {
     float *c64 = nullptr;   // [K][M] (re, im)
     double *soa = nullptr;  // [ntiles][2M+1][TILE]
+    double *fz = nullptr;   // fused-kernel layout [tiles of 224 rows][9][224] (M = 4 only)
 };
 
 struct Workspace {
@@ -60,6 +61,7 @@ struct music_b200 {
     cudaStream_t s_cov = nullptr, s_scan = nullptr;
     cudaEvent_t ev_in = nullptr;
     bool pipeline = false;   // MUSIC_B200_PIPE=1 enables the sub-batch pipeline (launch-bound at 10k windows: off)
+    long long *fused_trace = nullptr;  // MUSIC_B200_TRACE=1: per-CTA clock64 trace of the fused kernel (tools/fused_trace.py)
     bool fused = true;       // MUSIC_B200_FUSED=0 forces the three-kernel path
     bool scan_fast = true;   // MUSIC_B200_SCAN=general disables the specialised n == 1 kernel
     int cov_tma_stages = 6;  // 0 = LDG tile kernel (MUSIC_B200_COV=ldg), 4 or 6 = TMA ring depth
@@ -116,6 +118,11 @@ int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t s
     const int ntiles = (int)table_tiles(h->K);
     prep_table_kernel<<<ntiles, TILE, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.soa, (int)h->K, (int)h->m);
     h->launches++;
+    if (t.fz) {
+        const int rows = fused_scan_rows((int)h->K);
+        prep_table_fused_kernel<<<(rows + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.fz, (int)h->K);
+        h->launches++;
+    }
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(st));
     return MUSIC_B200_OK;
@@ -292,8 +299,8 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
         const int grid = std::min<int>(h->sm_count, (int)((nwindows + FZ_COV_WARPS - 1) / FZ_COV_WARPS));
-        music4_fused_kernel<<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, h->table[h->cur_table].soa, (int)nwindows, (int)h->N,
-                                                             (int)h->K, PeakOut{d_ang, d_lvl, d_bins});
+        music4_fused_kernel<<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, h->table[h->cur_table].fz, (int)nwindows, (int)h->N,
+                                                             (int)h->K, PeakOut{d_ang, d_lvl, d_bins}, h->fused_trace);
         h->launches++;
         if (tev) for (int i = 1; i < 5; ++i) cudaEventRecord(tev[i], st);
         CU(h, cudaGetLastError());
@@ -389,6 +396,16 @@ const char *music_b200_last_error(const music_b200 *h)
 
 uint64_t music_b200_launch_count(const music_b200 *h) { return h ? h->launches.load() : 0; }
 
+int music_b200_debug_fused_trace(music_b200 *h, long long *host_out, int max_ctas)
+{
+    if (!h || !host_out || !h->fused_trace) return MUSIC_B200_EINVAL;
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    CU(h, cudaMemcpy(host_out, h->fused_trace, (size_t)std::min(max_ctas, 1024) * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return MUSIC_B200_OK;
+}
+
 int music_b200_set_stage_timing(music_b200 *h, int enable)
 {
     if (!h) return MUSIC_B200_EINVAL;
@@ -455,6 +472,7 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
             CU(h, cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming));
             CU(h, cudaMalloc(&h->table[i].c64, (size_t)resolution * m * 2 * sizeof(float)));
             CU(h, cudaMalloc(&h->table[i].soa, soa_doubles(resolution, m) * sizeof(double)));
+            if (m == 4) CU(h, cudaMalloc(&h->table[i].fz, (size_t)fused_scan_rows((int)resolution) * FZ_TCOMP * sizeof(double)));
         }
         CU(h, cudaStreamCreateWithFlags(&h->s_cov, cudaStreamNonBlocking));
         CU(h, cudaStreamCreateWithFlags(&h->s_scan, cudaStreamNonBlocking));
@@ -472,6 +490,10 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         }
         if (const char *e = getenv("MUSIC_B200_SCAN")) h->scan_fast = strcmp(e, "general") != 0;
         if (const char *e = getenv("MUSIC_B200_FUSED")) h->fused = atoi(e) != 0;
+        if (getenv("MUSIC_B200_TRACE")) {
+            CU(h, cudaMalloc(&h->fused_trace, 16 * sizeof(long long) * 1024));
+            CU(h, cudaMemset(h->fused_trace, 0, 16 * sizeof(long long) * 1024));
+        }
         CU(h, cudaFuncSetAttribute(music4_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 6 * COV_CHUNK));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 4 * COV_CHUNK));
@@ -579,8 +601,9 @@ void music_b200_destroy(music_b200 *h)
     if (h->s_cov) cudaStreamDestroy(h->s_cov);
     if (h->s_scan) cudaStreamDestroy(h->s_scan);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
+    cudaFree(h->fused_trace);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(h->table[i].c64); cudaFree(h->table[i].soa);
+        cudaFree(h->table[i].c64); cudaFree(h->table[i].soa); cudaFree(h->table[i].fz);
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
         if (h->done[i]) cudaEventDestroy(h->done[i]);
     }

@@ -27,7 +27,10 @@ constexpr int FZ_THREADS = 32 * (FZ_COV_WARPS + 1 + FZ_SCAN_WARPS);  // 512
 constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224 bins per pass iteration
 constexpr int FZ_Q = 64;        // window queue slots per CTA
 constexpr int FZ_WPT = 4;       // windows per scan pass
-constexpr int FZ_STAGES = 5;    // 4 KiB TMA stages per covariance warp
+constexpr int FZ_STAGES = 4;    // 4 KiB TMA stages per covariance warp
+constexpr int FZ_TS = 3;        // steering-table tile stages (TMA ring shared by the scan warps)
+constexpr int FZ_TCOMP = 9;     // doubles per table row for M = 4: Re/Im a_0..a_3, ||a||^2
+constexpr int FZ_TILE_BYTES = FZ_TCOMP * FZ_SCAN_THREADS * 8;  // 16128 B: one 224-row tile, [comp][224]
 
 struct FusedCtl {               // shared-memory control block
     unsigned cov_seq;           // tickets handed to covariance warps
@@ -44,8 +47,12 @@ constexpr size_t FZ_OFF_WIN = 1088;                           // int win[FZ_Q]
 constexpr size_t FZ_OFF_RED = FZ_OFF_WIN + 4 * FZ_Q;          // reduction scratch: 7 warps x 4 x (double, int)
 constexpr size_t FZ_OFF_RQ = 2048;                            // double Rq[FZ_Q][32]
 constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
-constexpr size_t FZ_OFF_RING = FZ_OFF_VQ + (size_t)FZ_Q * 256;
+constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256;   // FZ_TS table tiles
+constexpr size_t FZ_OFF_RING = (FZ_OFF_TBL + (size_t)FZ_TS * FZ_TILE_BYTES + 127) / 128 * 128;
 constexpr size_t FZ_SMEM = FZ_OFF_RING + (size_t)FZ_COV_WARPS * FZ_STAGES * COV_CHUNK;
+constexpr size_t FZ_OFF_TBAR = 512;                            // uint64 tfull[FZ_TS], tempty[FZ_TS]
+static_assert(FZ_COV_WARPS * FZ_STAGES * 8 <= FZ_OFF_TBAR, "covariance barriers overlap the table barriers");
+static_assert(FZ_SMEM <= 227 * 1024, "fused kernel shared memory");
 static_assert(FZ_OFF_RED + 12 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_RQ, "control area overflow");
 
 __device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_SCAN_THREADS) : "memory"); }
@@ -54,9 +61,29 @@ __device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;"
 // least that many rows (prep_table_kernel pads whole TILE-row tiles with ||a||^2 = +inf).
 __host__ __device__ inline int fused_scan_rows(int K) { return (K + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS * FZ_SCAN_THREADS; }
 
-__global__ void __launch_bounds__(FZ_THREADS, 1)
-music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa, int W, int N, int K, PeakOut out)
+// Steering table in the fused kernel's layout: tiles of 224 rows, [tile][comp][224] fp64, so that one
+// 1-D bulk copy brings a whole tile; rows >= K are padding with ||a||^2 = +inf (never win).
+__global__ void prep_table_fused_kernel(const float2 *__restrict__ tab, double *__restrict__ tbl, int K)
 {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;  // row
+    if (r >= fused_scan_rows(K)) return;
+    double *base = tbl + (size_t)(r / FZ_SCAN_THREADS) * (FZ_TCOMP * FZ_SCAN_THREADS) + (r % FZ_SCAN_THREADS);
+    double na = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        double re = 0.0, im = 0.0;
+        if (r < K) { const float2 a = tab[(size_t)r * 4 + i]; re = a.x; im = a.y; }
+        base[(size_t)(2 * i) * FZ_SCAN_THREADS] = re;
+        base[(size_t)(2 * i + 1) * FZ_SCAN_THREADS] = im;
+        na = fma(re, re, fma(im, im, na));
+    }
+    base[(size_t)8 * FZ_SCAN_THREADS] = (r < K) ? na : __longlong_as_double(0x7ff0000000000000LL);
+}
+
+__global__ void __launch_bounds__(FZ_THREADS, 1)
+music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl /* [niter][9][224] */, int W, int N, int K, PeakOut out,
+                    long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */)
+{
+    const long long t_start = clock64();
     extern __shared__ __align__(128) unsigned char fz_smem[];
     FusedCtl *ctl = reinterpret_cast<FusedCtl *>(fz_smem + FZ_OFF_CTL);
     int *qwin = reinterpret_cast<int *>(fz_smem + FZ_OFF_WIN);
@@ -67,6 +94,13 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
     if (threadIdx.x == 0) {
         ctl->cov_seq = 0; ctl->cov_pub = 0; ctl->eig_done = 0; ctl->scan_done = 0; ctl->cov_finished = 0;
         ctl->batch_start = 0; ctl->batch_cnt = 0;
+        const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR);
+        for (int s = 0; s < FZ_TS; ++s) {
+            mbar_init(tb0 + 8 * s, 1);                          // tfull: one producer arrival + tx bytes
+            mbar_init(tb0 + 8 * (FZ_TS + s), FZ_SCAN_WARPS);    // tempty: one arrival per scan warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
@@ -157,8 +191,10 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
             }
         }
         if (lane == 0) atomicAdd((unsigned *)&ctl->cov_finished, 1u);
+        if (dbg && lane == 0) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;  // this covariance warp is done
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
+        long long eig_busy = 0, eig_rounds = 0;
         for (;;) {
             const unsigned done = ctl->eig_done;
             const unsigned avail = ctl->cov_pub - done;
@@ -168,6 +204,7 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
                 continue;
             }
             __threadfence_block();
+            const long long t0 = clock64();
             const unsigned cnt = min(avail, 32u);
             if ((unsigned)lane < cnt) {
                 const unsigned slot = (done + lane) % FZ_Q;
@@ -177,6 +214,13 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
             __threadfence_block();
             if (lane == 0) ctl->eig_done = done + cnt;
             __syncwarp();
+            eig_busy += clock64() - t0;
+            ++eig_rounds;
+        }
+        if (dbg && lane == 0) {
+            dbg[blockIdx.x * 16 + 8] = clock64() - t_start;
+            dbg[blockIdx.x * 16 + 9] = eig_busy;
+            dbg[blockIdx.x * 16 + 10] = eig_rounds;
         }
     } else {
         // ================= scan warps =================
@@ -187,6 +231,9 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
         int *redk = reinterpret_cast<int *>(fz_smem + FZ_OFF_RED + 8 * FZ_SCAN_WARPS * FZ_WPT);
         const uint32_t Vq0 = smem_u32(Vq);
         const int niter = (K + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS;
+        const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR), tbuf0 = smem_u32(fz_smem + FZ_OFF_TBL);
+        unsigned T = 0;  // table tiles consumed so far (identical in every scan thread)
+        long long scan_busy = 0, scan_passes = 0;
         for (;;) {
             if (st == 0) {
                 unsigned start, cnt;
@@ -204,33 +251,44 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
             bar_sync_scan();
             const unsigned start = ctl->batch_start, cnt = ctl->batch_cnt;
             if (cnt == 0) break;
+            const long long t0 = clock64();
             uint32_t ev[FZ_WPT];  // shared address of each window's eigenvectors (clamped duplicates beyond cnt)
 #pragma unroll
             for (int b = 0; b < FZ_WPT; ++b) ev[b] = Vq0 + 8 * vsz * ((start + min((unsigned)b, cnt - 1)) % FZ_Q);
             PeakState<FZ_WPT> ps;
             ps.reset();
 
-            // table entry of this thread's bin, prefetched one iteration ahead
-            double nar[M], nai[M], nna;
-            {
-                const double *tb = soa + (size_t)(st / TILE) * (2 * M + 1) * TILE + (st % TILE);
-#pragma unroll
-                for (int i = 0; i < M; ++i) { nar[i] = tb[(size_t)(2 * i) * TILE]; nai[i] = tb[(size_t)(2 * i + 1) * TILE]; }
-                nna = tb[(size_t)(2 * M) * TILE];
-            }
-            for (int it = 0; it < niter; ++it) {
-                const int k = it * FZ_SCAN_THREADS + st;
-                double ar[M], ai[M];
-#pragma unroll
-                for (int i = 0; i < M; ++i) { ar[i] = nar[i]; ai[i] = nai[i]; }
-                const double na = nna;
-                if (it + 1 < niter) {
-                    const int kn = k + FZ_SCAN_THREADS;
-                    const double *tb = soa + (size_t)(kn / TILE) * (2 * M + 1) * TILE + (kn % TILE);
-#pragma unroll
-                    for (int i = 0; i < M; ++i) { nar[i] = tb[(size_t)(2 * i) * TILE]; nai[i] = tb[(size_t)(2 * i + 1) * TILE]; }
-                    nna = tb[(size_t)(2 * M) * TILE];
+            // Steering-table tiles stream through a FZ_TS-deep TMA ring shared by the scan warps (the
+            // table lives in L2, but under the covariance warps' HBM stream an L2 hit costs > 1000
+            // cycles - far more than one tile of arithmetic).  T counts tiles since kernel start:
+            // slot = T % FZ_TS, tfull parity = (T / FZ_TS) & 1; a tile is released by one arrival per
+            // scan warp on tempty, which the producer (thread 0 of the scan group) awaits before refill.
+            for (int it = 0; it < niter; ++it, ++T) {
+                const int slot = (int)(T % FZ_TS);
+                if (st == 0) {
+                    // keep the ring full: tiles it .. it+FZ_TS-1 of this pass (prologue at it == 0)
+                    for (int a = (it == 0 ? 0 : FZ_TS - 1); a < FZ_TS; ++a) {
+                        const int ia = it + a;
+                        if (ia >= niter) break;
+                        const unsigned Ta = T + a;
+                        const int sa = (int)(Ta % FZ_TS);
+                        if (Ta >= FZ_TS) while (!mbar_try_wait(tb0 + 8 * (FZ_TS + sa), (uint32_t)((Ta / FZ_TS - 1) & 1))) {}
+                        mbar_expect_tx(tb0 + 8 * sa, FZ_TILE_BYTES);
+                        bulk_g2s(tbuf0 + sa * FZ_TILE_BYTES, tbl + (size_t)ia * (FZ_TCOMP * FZ_SCAN_THREADS), FZ_TILE_BYTES, tb0 + 8 * sa);
+                    }
                 }
+                while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
+                const int k = it * FZ_SCAN_THREADS + st;
+                const uint32_t row = tbuf0 + slot * FZ_TILE_BYTES + 8 * st;
+                double ar[M], ai[M], na;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ar[i]) : "r"(row + 8 * FZ_SCAN_THREADS * (2 * i)));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ai[i]) : "r"(row + 8 * FZ_SCAN_THREADS * (2 * i + 1)));
+                }
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(na) : "r"(row + 8 * FZ_SCAN_THREADS * 8));
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
                 scan_bin<M, FZ_WPT>(ar, ai, na, k, ev, ps);
             }
 #pragma unroll
@@ -267,6 +325,13 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ soa
                 __threadfence_block();
                 ctl->scan_done = start + cnt;
             }
+            scan_busy += clock64() - t0;
+            ++scan_passes;
+        }
+        if (dbg && st == 0) {
+            dbg[blockIdx.x * 16 + 11] = clock64() - t_start;
+            dbg[blockIdx.x * 16 + 12] = scan_busy;
+            dbg[blockIdx.x * 16 + 13] = scan_passes;
         }
     }
 }

@@ -107,6 +107,10 @@ uint64_t music_b200_launch_count(const music_b200 *h);
 int music_b200_set_stage_timing(music_b200 *h, int enable);
 int music_b200_get_stage_times(music_b200 *h, double *ms4, uint64_t *chunks);
 
+/* Debug: copy the fused kernel's per-CTA clock64 trace (16 int64 per CTA; only when the handle
+ * was created with MUSIC_B200_TRACE=1 in the environment). */
+int music_b200_debug_fused_trace(music_b200 *h, long long *host_out, int max_ctas);
+
 /* Last error text for this handle; h == NULL returns the last create() failure. */
 const char *music_b200_last_error(const music_b200 *h);
 

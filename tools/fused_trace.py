@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Per-CTA clock64 trace of the fused kernel (MUSIC_B200_TRACE=1): when each role finished and how
+busy the eigensolver / scan warps were.  Run on the GPU box: python tools/fused_trace.py"""
+import os
+import sys
+
+os.environ["MUSIC_B200_TRACE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import bench
+from gr_baz_b200 import synth
+from gr_baz_b200.music_doa import music_doa
+
+cfg, W = bench.workload(2)
+resp, _ = bench.table_for(cfg)
+dev = torch.device("cuda:0")
+d_in = synth.gen_windows_torch(cfg, synth.BASE_SEED + 2, 0, W, dev)
+blk = music_doa(cfg["m"], cfg["n"], cfg["nsamples"], resp, cfg["resolution"])
+a = torch.empty((W, 1), dtype=torch.float32, device=dev)
+l = torch.empty_like(a)
+b = torch.empty((W, 1), dtype=torch.int32, device=dev)
+for _ in range(3):
+    blk.process_device(d_in.data_ptr(), W, a.data_ptr(), l.data_ptr(), None, b.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+tr = np.zeros((148, 16), np.int64)
+blk._lib.music_b200_debug_fused_trace(blk._h, tr.ctypes.data, 148)
+cov_end = tr[:, :8].max(axis=1)
+print("cycles (mean over CTAs):")
+print("  last cov warp done   %9.0f   (first cov warp done %9.0f)" % (cov_end.mean(), tr[:, :8].min(axis=1).mean()))
+print("  eig warp exit        %9.0f   busy %9.0f in %5.1f rounds -> %7.0f cyc/round" % (tr[:, 8].mean(), tr[:, 9].mean(), tr[:, 10].mean(), (tr[:, 9] / np.maximum(tr[:, 10], 1)).mean()))
+print("  scan warps exit      %9.0f   busy %9.0f in %5.1f passes -> %7.0f cyc/pass" % (tr[:, 11].mean(), tr[:, 12].mean(), tr[:, 13].mean(), (tr[:, 12] / np.maximum(tr[:, 13], 1)).mean()))
+print("  tail after last cov  %9.0f" % (tr[:, 11] - cov_end).mean())
