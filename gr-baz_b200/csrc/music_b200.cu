@@ -32,7 +32,8 @@ std::string g_create_error;
 struct DeviceTable {
     float *c64 = nullptr;   // [K][M] (re, im)
     double *soa = nullptr;  // [ntiles][2M+1][TILE]
-    double *fz = nullptr;   // fused-kernel layout [tiles of 224 rows][9][224] (M = 4 only)
+    unsigned char *fz = nullptr;  // fused kernel's tensor-core screen layout (music_fused.cuh, M = 4 only)
+    float *na_max = nullptr;      // max ||a||^2 over the table rows (screen threshold)
 };
 
 struct Workspace {
@@ -106,9 +107,8 @@ int fail(music_b200 *h, int code, const char *fmt, ...)
                         "%s failed: %s", #expr, cudaGetErrorString(e_));                        \
     } while (0)
 
-// Table rows are padded (||a||^2 = +inf) to whole TILE-row tiles covering both K and the rows the
-// fused kernel's 224-thread scan touches.
-uint32_t table_tiles(uint32_t K) { return (uint32_t)((std::max<int>((int)K, fused_scan_rows((int)K)) + TILE - 1) / TILE); }
+// Table rows are padded (||a||^2 = +inf) to whole TILE-row tiles.
+uint32_t table_tiles(uint32_t K) { return (uint32_t)((K + TILE - 1) / TILE); }
 size_t soa_doubles(uint32_t K, uint32_t M) { return (size_t)table_tiles(K) * (2 * M + 1) * TILE; }
 
 int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t st)
@@ -119,8 +119,9 @@ int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t s
     prep_table_kernel<<<ntiles, TILE, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.soa, (int)h->K, (int)h->m);
     h->launches++;
     if (t.fz) {
-        const int rows = fused_scan_rows((int)h->K);
-        prep_table_fused_kernel<<<(rows + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.fz, (int)h->K);
+        const int threads = fused_tiles((int)h->K) * (FZ_BINS / 16) * 32;
+        CU(h, cudaMemsetAsync(t.na_max, 0, sizeof(float), st));
+        prep_table_tc_kernel<<<(threads + 255) / 256, 256, 0, st>>>(t.c64, t.fz, t.na_max, (int)h->K);
         h->launches++;
     }
     CU(h, cudaGetLastError());
@@ -299,7 +300,8 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
         const int grid = std::min<int>(h->sm_count, (int)((nwindows + FZ_COV_WARPS - 1) / FZ_COV_WARPS));
-        music4_fused_kernel<<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, h->table[h->cur_table].fz, (int)nwindows, (int)h->N,
+        const DeviceTable &tb = h->table[h->cur_table];
+        music4_fused_kernel<<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, tb.fz, tb.c64, tb.na_max, (int)nwindows, (int)h->N,
                                                              (int)h->K, PeakOut{d_ang, d_lvl, d_bins}, h->fused_trace);
         h->launches++;
         if (tev) for (int i = 1; i < 5; ++i) cudaEventRecord(tev[i], st);
@@ -472,7 +474,10 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
             CU(h, cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming));
             CU(h, cudaMalloc(&h->table[i].c64, (size_t)resolution * m * 2 * sizeof(float)));
             CU(h, cudaMalloc(&h->table[i].soa, soa_doubles(resolution, m) * sizeof(double)));
-            if (m == 4) CU(h, cudaMalloc(&h->table[i].fz, (size_t)fused_scan_rows((int)resolution) * FZ_TCOMP * sizeof(double)));
+            if (m == 4) {
+                CU(h, cudaMalloc(&h->table[i].fz, fused_table_bytes((int)resolution)));
+                CU(h, cudaMalloc(&h->table[i].na_max, sizeof(float)));
+            }
         }
         CU(h, cudaStreamCreateWithFlags(&h->s_cov, cudaStreamNonBlocking));
         CU(h, cudaStreamCreateWithFlags(&h->s_scan, cudaStreamNonBlocking));
@@ -603,7 +608,7 @@ void music_b200_destroy(music_b200 *h)
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->fused_trace);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(h->table[i].c64); cudaFree(h->table[i].soa); cudaFree(h->table[i].fz);
+        cudaFree(h->table[i].c64); cudaFree(h->table[i].soa); cudaFree(h->table[i].fz); cudaFree(h->table[i].na_max);
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
         if (h->done[i]) cudaEventDestroy(h->done[i]);
     }

@@ -1,21 +1,34 @@
-// music_fused.cuh - FUSED persistent kernel for the headline shape class (M = 4, n = 1, peak
-// outputs only): K1 + K2 + K3 in one launch, one CTA per SM, warp-specialised; R and the
-// eigenvectors never leave shared memory.
+// music_fused.cuh - FUSED persistent kernel for the headline shape class (M = 4 antennas, n = 1
+// source, peak outputs only): covariance + eigendecomposition + pseudospectrum scan + peak pick in
+// ONE launch, one CTA per SM, warp-specialised.  R and the eigenvectors never leave shared memory.
 //
-//   warps 0..7   covariance: per-warp TMA ring exactly as cov4_tma_kernel; a finished window's R
-//                is pushed into a 64-slot shared-memory queue (in-order publish).
+//   warps 0..7   covariance (FP64 pipe): per-warp TMA ring exactly as cov4_tma_kernel; a finished
+//                window's R is pushed into a 64-slot shared-memory queue (in-order publish).
 //   warp  8      eigensolver: one lane per queued window (up to 32 at once), cyclic Jacobi
 //                (herm_eig_body<4>), eigenvectors written next to the queue slot.
-//   warps 9..15  pseudospectrum scan + peak pick of up to 4 windows per pass: thread <-> bin,
-//                same hot loop as scan_peak1_kernel, results merged over the 7 warps and written
-//                to global (angle, level, bin).
+//   warps 9..15  pseudospectrum scan + peak pick, up to 4 windows per pass:
+//                  1. SCREEN on the tensor cores: c_k = e_s^H a_k for all bins k and the 4 windows as a
+//                     [bins x 8] x [8 x 8] product in 3xTF32 (mma.sync m16n8k8, hi/lo split of both
+//                     operands, fp32 accumulate), d~_k = ||a_k||^2 - |c_k|^2 in fp32.  The FP64 pipe -
+//                     which the covariance warps need - is not touched.
+//                  2. the screen's error is bounded by FZ_B * ||a_k||^2 (derivation below), so only
+//                     bins with d~_k - B||a_k||^2 <= min_k d~_k + B max||a||^2 can hold the fp64
+//                     minimum; they are re-evaluated EXACTLY in fp64 (same complement/direct formula as
+//                     the unfused kernels) and the peak is picked among them with the reference's rule
+//                     (strength desc, bin asc, strict '>', /root/reference/lib/baz_music_doa.cc:129-141).
+//                     Typically 2-30 bins per window; if a window has more than FZ_CMAX candidates (flat
+//                     spectra, e.g. an all-zero window) every bin is evaluated in fp64 instead.
+//                The result is therefore bit-identical to an all-fp64 scan.
 //
-// The stages overlap in time on every SM: while the covariance warps keep HBM busy (their FP64
-// demand is ~1/3 of the pipe), the scan warps fill the remaining FP64 issue slots.  Counters in
-// shared memory (cov_pub >= eig_done >= scan_done) hand windows from stage to stage.
+// Screen error bound.  a is stored in fp32 exactly (the block's table IS complex64); e is rounded
+// to fp32 (2^-24).  x = x_hi + x_lo + r with x_hi = tf32(x), x_lo = tf32(x - x_hi), |r| <= 2^-22|x|.
+// The three products hi*hi, hi*lo, lo*hi are exact in fp32 (11-bit x 11-bit significands); the
+// dropped lo*lo term is <= 2^-22 |a||e|.  With <= 24 fp32 accumulations (<= 2^-23 each, truncation
+// allowed), |c~ - c| <= 2^-19 sum|a_i||e_i| <= 2^-19 ||a||.  Then ||c~|^2 - |c|^2| <= 2^-18 ||a||^2 (+ 2^-22
+// for the fp32 squares and the subtraction from fl32(||a||^2)).  FZ_B = 2^-16 leaves a 3.5x margin.
 //
-// Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does
-// per window except the optional spectrum port).
+// Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does per
+// window except the optional spectrum port).
 #pragma once
 #include "music_kernels.cuh"
 
@@ -24,13 +37,15 @@ namespace music {
 constexpr int FZ_COV_WARPS = 8;
 constexpr int FZ_SCAN_WARPS = 7;
 constexpr int FZ_THREADS = 32 * (FZ_COV_WARPS + 1 + FZ_SCAN_WARPS);  // 512
-constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224 bins per pass iteration
+constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224
+constexpr int FZ_BINS = 224;    // table rows per TMA tile = 14 MMA tiles of 16 rows, 2 per scan warp
 constexpr int FZ_Q = 64;        // window queue slots per CTA
-constexpr int FZ_WPT = 4;       // windows per scan pass
+constexpr int FZ_WPT = 4;       // windows per scan pass (the 8 MMA columns = 4 windows x {re, im})
 constexpr int FZ_STAGES = 4;    // 4 KiB TMA stages per covariance warp
 constexpr int FZ_TS = 3;        // steering-table tile stages (TMA ring shared by the scan warps)
-constexpr int FZ_TCOMP = 9;     // doubles per table row for M = 4: Re/Im a_0..a_3, ||a||^2
-constexpr int FZ_TILE_BYTES = FZ_TCOMP * FZ_SCAN_THREADS * 8;  // 16128 B: one 224-row tile, [comp][224]
+constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * 1024 + FZ_BINS * 4;  // 14 fragment tiles + fp32 ||a||^2 = 15232
+constexpr int FZ_CMAX = 32;     // exact candidates kept per window before falling back to a full fp64 scan
+constexpr float FZ_B = 1.52587890625e-05f;  // 2^-16, see "Screen error bound"
 
 struct FusedCtl {               // shared-memory control block
     unsigned cov_seq;           // tickets handed to covariance warps
@@ -42,46 +57,101 @@ struct FusedCtl {               // shared-memory control block
     unsigned pad;
 };
 
+constexpr size_t FZ_OFF_TBAR = 512;     // uint64 tfull[FZ_TS], tempty[FZ_TS]
 constexpr size_t FZ_OFF_CTL = 1024;
-constexpr size_t FZ_OFF_WIN = 1088;                           // int win[FZ_Q]
-constexpr size_t FZ_OFF_RED = FZ_OFF_WIN + 4 * FZ_Q;          // reduction scratch: 7 warps x 4 x (double, int)
-constexpr size_t FZ_OFF_RQ = 2048;                            // double Rq[FZ_Q][32]
+constexpr size_t FZ_OFF_WIN = 1088;     // int qwin[FZ_Q]
+constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][4]
+constexpr size_t FZ_OFF_CCNT = 1472;    // int cand_cnt[4]
+constexpr size_t FZ_OFF_CBIN = 1536;    // int cand_bin[4][FZ_CMAX]
+constexpr size_t FZ_OFF_CP = 2048;      // double candP[4][FZ_CMAX]
+constexpr size_t FZ_OFF_RED = 3072;     // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
+constexpr size_t FZ_OFF_RQ = 4096;                            // double Rq[FZ_Q][32]
 constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
-constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256;   // FZ_TS table tiles
+constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256; // FZ_TS table tiles
 constexpr size_t FZ_OFF_RING = (FZ_OFF_TBL + (size_t)FZ_TS * FZ_TILE_BYTES + 127) / 128 * 128;
 constexpr size_t FZ_SMEM = FZ_OFF_RING + (size_t)FZ_COV_WARPS * FZ_STAGES * COV_CHUNK;
-constexpr size_t FZ_OFF_TBAR = 512;                            // uint64 tfull[FZ_TS], tempty[FZ_TS]
 static_assert(FZ_COV_WARPS * FZ_STAGES * 8 <= FZ_OFF_TBAR, "covariance barriers overlap the table barriers");
+static_assert(FZ_OFF_CBIN + 4 * 4 * FZ_CMAX <= FZ_OFF_CP && FZ_OFF_CP + 8 * 4 * FZ_CMAX <= FZ_OFF_RED, "scan scratch layout");
 static_assert(FZ_SMEM <= 227 * 1024, "fused kernel shared memory");
-static_assert(FZ_OFF_RED + 12 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_RQ, "control area overflow");
+static_assert(FZ_TILE_BYTES % 16 == 0, "bulk copy size");
 
 __device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_SCAN_THREADS) : "memory"); }
 
-// Bins covered by the scan warps per window: niter * 224; the steering table must be padded to at
-// least that many rows (prep_table_kernel pads whole TILE-row tiles with ||a||^2 = +inf).
-__host__ __device__ inline int fused_scan_rows(int K) { return (K + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS * FZ_SCAN_THREADS; }
+__host__ __device__ inline int fused_tiles(int K) { return (K + FZ_BINS - 1) / FZ_BINS; }
+__host__ __device__ inline size_t fused_table_bytes(int K) { return (size_t)fused_tiles(K) * FZ_TILE_BYTES; }
 
-// Steering table in the fused kernel's layout: tiles of 224 rows, [tile][comp][224] fp64, so that one
-// 1-D bulk copy brings a whole tile; rows >= K are padding with ||a||^2 = +inf (never win).
-__global__ void prep_table_fused_kernel(const float2 *__restrict__ tab, double *__restrict__ tbl, int K)
+__device__ __forceinline__ uint32_t to_tf32(float x)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;  // row
-    if (r >= fused_scan_rows(K)) return;
-    double *base = tbl + (size_t)(r / FZ_SCAN_THREADS) * (FZ_TCOMP * FZ_SCAN_THREADS) + (r % FZ_SCAN_THREADS);
-    double na = 0.0;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// Steering table in the tensor-core screen's layout.  Per 224-row tile: 14 MMA A-fragment tiles
+// (16 rows x 8 columns; the complex64 row [Re a0, Im a0, .., Re a3, Im a3] IS the A row), stored in
+// fragment order - lane l holds {hi a0..a3, lo a0..a3} with a0 = A[g][t], a1 = A[g+8][t],
+// a2 = A[g][t+4], a3 = A[g+8][t+4], g = l/4, t = l%4 - followed by fl32(||a||^2) per row
+// (+inf for padding rows, which therefore never win).  na_max = max ||a||^2 over the K real rows.
+__global__ void prep_table_tc_kernel(const float *__restrict__ tab, unsigned char *__restrict__ tbl, float *__restrict__ na_max,
+                                     int K)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (16-row tile, lane)
+    const int tile16 = idx >> 5, lane = idx & 31;
+    const int ntile16 = fused_tiles(K) * (FZ_BINS / 16);
+    if (tile16 >= ntile16) return;
+    const int g = lane >> 2, t = lane & 3;
+    unsigned char *tile = tbl + (size_t)(tile16 / (FZ_BINS / 16)) * FZ_TILE_BYTES;
+    float *frag = reinterpret_cast<float *>(tile) + (size_t)(tile16 % (FZ_BINS / 16)) * 256 + lane * 8;
+    const int rows[4] = {g, g + 8, g, g + 8};
+    const int cols[4] = {t, t, t + 4, t + 4};
     for (int i = 0; i < 4; ++i) {
-        double re = 0.0, im = 0.0;
-        if (r < K) { const float2 a = tab[(size_t)r * 4 + i]; re = a.x; im = a.y; }
-        base[(size_t)(2 * i) * FZ_SCAN_THREADS] = re;
-        base[(size_t)(2 * i + 1) * FZ_SCAN_THREADS] = im;
-        na = fma(re, re, fma(im, im, na));
+        const int bin = tile16 * 16 + rows[i];
+        const float v = bin < K ? tab[(size_t)bin * 8 + cols[i]] : 0.f;
+        const float hi = __uint_as_float(to_tf32(v));
+        const float lo = __uint_as_float(to_tf32(v - hi));
+        frag[i] = hi;
+        frag[4 + i] = lo;
     }
-    base[(size_t)8 * FZ_SCAN_THREADS] = (r < K) ? na : __longlong_as_double(0x7ff0000000000000LL);
+    if (lane < 16) {  // ||a||^2 of row `lane` of this 16-row tile, same fma order as prep_table_kernel
+        const int bin = tile16 * 16 + lane;
+        double na = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            double re = 0.0, im = 0.0;
+            if (bin < K) { re = tab[(size_t)bin * 8 + 2 * i]; im = tab[(size_t)bin * 8 + 2 * i + 1]; }
+            na = fma(re, re, fma(im, im, na));
+        }
+        float *na32 = reinterpret_cast<float *>(tile + (FZ_BINS / 16) * 1024) + (tile16 % (FZ_BINS / 16)) * 16 + lane;
+        if (bin < K) {
+            const float f = (float)na;
+            *na32 = f;
+            atomicMax(reinterpret_cast<int *>(na_max), __float_as_int(f));  // non-negative floats order like ints
+        } else {
+            *na32 = __int_as_float(0x7f800000);
+        }
+    }
+}
+
+// Exact fp64 strength of bin k for the window whose eigenvectors sit at shared address `ev`:
+// the same formula (and the same ||a||^2 fma order) as the unfused kernels.
+__device__ __forceinline__ double fused_exact_P(const float *__restrict__ tab_c64, int k, uint32_t ev)
+{
+    const float4 *row = reinterpret_cast<const float4 *>(tab_c64 + (size_t)k * 8);
+    const float4 x0 = __ldg(row), x1 = __ldg(row + 1);
+    double ar[4], ai[4];
+    ar[0] = x0.x; ai[0] = x0.y; ar[1] = x0.z; ai[1] = x0.w;
+    ar[2] = x1.x; ai[2] = x1.y; ar[3] = x1.z; ai[3] = x1.w;
+    double na = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) na = fma(ar[i], ar[i], fma(ai[i], ai[i], na));
+    double d = complement_denominator<4>(ar, ai, na, ev + 16 * 3 * 4);
+    if (d < COMPLEMENT_GUARD * na) d = direct_denominator<4>(ar, ai, ev);
+    return 1.0 / d;
 }
 
 __global__ void __launch_bounds__(FZ_THREADS, 1)
-music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl /* [niter][9][224] */, int W, int N, int K, PeakOut out,
-                    long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */)
+music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restrict__ tbl /* fused_table_bytes(K) */,
+                    const float *__restrict__ tab_c64 /* [K][4] complex64 */, const float *__restrict__ na_max_p, int W, int N,
+                    int K, PeakOut out, long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */)
 {
     const long long t_start = clock64();
     extern __shared__ __align__(128) unsigned char fz_smem[];
@@ -113,7 +183,6 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl
         const size_t win_bytes = (size_t)N * 32;
         const int cpw = (int)((win_bytes + COV_CHUNK - 1) / COV_CHUNK);
         const int nwin = gw < W ? (W - gw + total_warps - 1) / total_warps : 0;
-        const long long total = (long long)nwin * cpw;
         const unsigned char *src0 = reinterpret_cast<const unsigned char *>(in);
         if (lane == 0) {
             for (int s = 0; s < FZ_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -121,77 +190,77 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncwarp();
-        auto issue = [&](long long c) {  // lane 0 only
-            const int j = (int)(c / cpw), q = (int)(c % cpw);
-            const size_t off = (size_t)q * COV_CHUNK;
+        // producer state (lane 0): next chunk to request = chunk iq of this warp's window number ij
+        int iq = 0, ij = 0, islot = 0;
+        auto issue = [&]() {
+            const size_t off = (size_t)iq * COV_CHUNK;
             const uint32_t bytes = (uint32_t)min((size_t)COV_CHUNK, win_bytes - off);
-            const int slot = (int)(c % FZ_STAGES);
-            const unsigned char *src = src0 + ((size_t)gw + (size_t)j * total_warps) * win_bytes + off;
-            mbar_expect_tx(bar0 + 8 * slot, bytes);
-            bulk_g2s(ring0 + slot * COV_CHUNK, src, bytes, bar0 + 8 * slot);
+            const unsigned char *src = src0 + ((size_t)gw + (size_t)ij * total_warps) * win_bytes + off;
+            mbar_expect_tx(bar0 + 8 * islot, bytes);
+            bulk_g2s(ring0 + islot * COV_CHUNK, src, bytes, bar0 + 8 * islot);
+            if (++iq == cpw) { iq = 0; ++ij; }
+            if (++islot == FZ_STAGES) islot = 0;
         };
         if (lane == 0)
-            for (long long c = 0; c < total && c < FZ_STAGES; ++c) issue(c);
+            for (int s = 0; s < FZ_STAGES && ij < nwin; ++s) issue();
         double acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        int q = 0, j = 0, slot = 0;
+        int slot = 0;
         uint32_t parity = 0;
-        for (long long c = 0; c < total; ++c) {
-            while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
-            const size_t off = (size_t)q * COV_CHUNK;
-            const int nsnap = (int)(min((size_t)COV_CHUNK, win_bytes - off) >> 5);
-            const float4 *buf = reinterpret_cast<const float4 *>(ring + (size_t)slot * COV_CHUNK);
-            if (nsnap == COV_CHUNK / 32) {
-                float4 xa[4], xb[4];
+        for (int j = 0; j < nwin; ++j) {
+            for (int q = 0; q < cpw; ++q) {
+                while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
+                const size_t off = (size_t)q * COV_CHUNK;
+                const int nsnap = (int)(min((size_t)COV_CHUNK, win_bytes - off) >> 5);
+                const float4 *buf = reinterpret_cast<const float4 *>(ring + (size_t)slot * COV_CHUNK);
+                if (nsnap == COV_CHUNK / 32) {
+                    float4 xa[4], xb[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    xa[u] = buf[2 * (lane + 32 * u)];
-                    xb[u] = buf[2 * (lane + 32 * u) + 1];
+                    for (int u = 0; u < 4; ++u) {
+                        xa[u] = buf[2 * (lane + 32 * u)];
+                        xb[u] = buf[2 * (lane + 32 * u) + 1];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cov4_accumulate(acc, xa[u], xb[u]);
+                } else {
+                    for (int s = lane; s < nsnap; s += 32) cov4_accumulate(acc, buf[2 * s], buf[2 * s + 1]);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) cov4_accumulate(acc, xa[u], xb[u]);
-            } else {
-                for (int s = lane; s < nsnap; s += 32) cov4_accumulate(acc, buf[2 * s], buf[2 * s + 1]);
+                __syncwarp();  // every lane is done reading the slot -> it may be refilled
+                if (lane == 0 && ij < nwin) issue();
+                if (++slot == FZ_STAGES) { slot = 0; parity ^= 1; }
             }
-            __syncwarp();
-            if (lane == 0 && c + FZ_STAGES < total) issue(c + FZ_STAGES);
-            if (++slot == FZ_STAGES) { slot = 0; parity ^= 1; }
-            if (++q == cpw) {
-                q = 0;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
-                if (lane == 0) {
-                    const unsigned seq = atomicAdd(&ctl->cov_seq, 1u);
-                    while (seq - ctl->scan_done >= (unsigned)FZ_Q) __nanosleep(100);  // queue slot free?
-                    const double dn = (double)N;
-                    double *Rw = Rq + (size_t)(seq % FZ_Q) * 32;
-                    Rw[0] = acc[0] / dn;   Rw[1] = 0.0;
-                    Rw[10] = acc[1] / dn;  Rw[11] = 0.0;
-                    Rw[20] = acc[2] / dn;  Rw[21] = 0.0;
-                    Rw[30] = acc[3] / dn;  Rw[31] = 0.0;
-                    int e = 4;
+            for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+            if (lane == 0) {
+                const unsigned seq = atomicAdd(&ctl->cov_seq, 1u);
+                while (seq - ctl->scan_done >= (unsigned)FZ_Q) __nanosleep(100);  // queue slot free?
+                const double dn = (double)N;
+                double *Rw = Rq + (size_t)(seq % FZ_Q) * 32;
+                Rw[0] = acc[0] / dn;   Rw[1] = 0.0;
+                Rw[10] = acc[1] / dn;  Rw[11] = 0.0;
+                Rw[20] = acc[2] / dn;  Rw[21] = 0.0;
+                Rw[30] = acc[3] / dn;  Rw[31] = 0.0;
+                int e = 4;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a)
+                for (int a = 0; a < 4; ++a)
 #pragma unroll
-                        for (int b = a + 1; b < 4; ++b) {
-                            const double re = acc[e] / dn, im = acc[e + 1] / dn;
-                            Rw[2 * (a * 4 + b)] = re;  Rw[2 * (a * 4 + b) + 1] = im;
-                            Rw[2 * (b * 4 + a)] = re;  Rw[2 * (b * 4 + a) + 1] = -im;
-                            e += 2;
-                        }
-                    qwin[seq % FZ_Q] = gw + j * total_warps;
-                    while (ctl->cov_pub != seq) {}  // publish in ticket order
-                    __threadfence_block();
-                    ctl->cov_pub = seq + 1;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-                ++j;
+                    for (int b = a + 1; b < 4; ++b) {
+                        const double re = acc[e] / dn, im = acc[e + 1] / dn;
+                        Rw[2 * (a * 4 + b)] = re;  Rw[2 * (a * 4 + b) + 1] = im;
+                        Rw[2 * (b * 4 + a)] = re;  Rw[2 * (b * 4 + a) + 1] = -im;
+                        e += 2;
+                    }
+                qwin[seq % FZ_Q] = gw + j * total_warps;
+                while (ctl->cov_pub != seq) {}  // publish in ticket order
+                __threadfence_block();
+                ctl->cov_pub = seq + 1;
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         }
         if (lane == 0) atomicAdd((unsigned *)&ctl->cov_finished, 1u);
-        if (dbg && lane == 0) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;  // this covariance warp is done
+        if (dbg && lane == 0 && warp < 7) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0;
@@ -224,16 +293,69 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl
         }
     } else {
         // ================= scan warps =================
-        constexpr int M = 4, vsz = 32;
         const int st = threadIdx.x - 32 * (FZ_COV_WARPS + 1);  // 0..223
         const int swarp = st >> 5;
-        double *redP = reinterpret_cast<double *>(fz_smem + FZ_OFF_RED);  // [7][4]
-        int *redk = reinterpret_cast<int *>(fz_smem + FZ_OFF_RED + 8 * FZ_SCAN_WARPS * FZ_WPT);
+        const int g = lane >> 2, t = lane & 3;                 // MMA fragment coordinates; t = this thread's window
+        float *redmin = reinterpret_cast<float *>(fz_smem + FZ_OFF_RMIN);
+        int *cand_cnt = reinterpret_cast<int *>(fz_smem + FZ_OFF_CCNT);
+        int *cand_bin = reinterpret_cast<int *>(fz_smem + FZ_OFF_CBIN);
+        double *candP = reinterpret_cast<double *>(fz_smem + FZ_OFF_CP);
+        double *redP = reinterpret_cast<double *>(fz_smem + FZ_OFF_RED);
+        int *redk = reinterpret_cast<int *>(fz_smem + FZ_OFF_RED + 8 * FZ_SCAN_WARPS);
         const uint32_t Vq0 = smem_u32(Vq);
-        const int niter = (K + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS;
+        const int ntile = fused_tiles(K);
         const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR), tbuf0 = smem_u32(fz_smem + FZ_OFF_TBL);
+        const float na_max = __ldg(na_max_p);
         unsigned T = 0;  // table tiles consumed so far (identical in every scan thread)
-        long long scan_busy = 0, scan_passes = 0;
+        long long scan_busy = 0, scan_passes = 0, scan_exact = 0, scan_fallbacks = 0, scan_ncand = 0;
+
+        // One sweep over the whole table through the TMA ring; f(row_g, d~_g, na_g, d~_g8, na_g8) per thread
+        // and MMA tile.  T counts tiles since kernel start: slot = T % FZ_TS, tfull parity =
+        // (T / FZ_TS) & 1; a tile is released by one arrival per scan warp on tempty, which the
+        // producer (thread 0 of the scan group) awaits before refilling the slot.
+        auto sweep = [&](const uint32_t bh0, const uint32_t bh1, const uint32_t bl0, const uint32_t bl1, auto &&f) {
+            for (int it = 0; it < ntile; ++it, ++T) {
+                const int slot = (int)(T % FZ_TS);
+                if (st == 0) {
+                    for (int a = (it == 0 ? 0 : FZ_TS - 1); a < FZ_TS; ++a) {
+                        const int ia = it + a;
+                        if (ia >= ntile) break;
+                        const unsigned Ta = T + a;
+                        const int sa = (int)(Ta % FZ_TS);
+                        if (Ta >= FZ_TS) while (!mbar_try_wait(tb0 + 8 * (FZ_TS + sa), (uint32_t)((Ta / FZ_TS - 1) & 1))) {}
+                        mbar_expect_tx(tb0 + 8 * sa, FZ_TILE_BYTES);
+                        bulk_g2s(tbuf0 + sa * FZ_TILE_BYTES, tbl + (size_t)ia * FZ_TILE_BYTES, FZ_TILE_BYTES, tb0 + 8 * sa);
+                    }
+                }
+                while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
+                const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int mt = swarp * 2 + m;  // MMA tile within the 224-row tile
+                    uint32_t ah[4], al[4];
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3]) : "r"(tile + mt * 1024 + lane * 32));
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(tile + mt * 1024 + lane * 32 + 16));
+                    float na0, na1;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na0) : "r"(tile + (FZ_BINS / 16) * 1024 + 4 * (mt * 16 + g)));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na1) : "r"(tile + (FZ_BINS / 16) * 1024 + 4 * (mt * 16 + g + 8)));
+                    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                    // small terms first: a_lo*e_hi, a_hi*e_lo, then a_hi*e_hi
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]), "r"(bh0), "r"(bh1));
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bl0), "r"(bl1));
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bh0), "r"(bh1));
+                    // (c0, c1) = (Re, Im) of e^H a for row g, window t; (c2, c3) the same for row g + 8
+                    const float d0 = na0 - fmaf(c0, c0, c1 * c1);
+                    const float d1 = na1 - fmaf(c2, c2, c3 * c3);
+                    f(it * FZ_BINS + mt * 16 + g, d0, na0, d1, na1);
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
+            }
+        };
+
         for (;;) {
             if (st == 0) {
                 unsigned start, cnt;
@@ -248,69 +370,74 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl
                 ctl->batch_cnt = cnt;
                 __threadfence_block();
             }
+            if (st < 4) cand_cnt[st] = 0;
             bar_sync_scan();
             const unsigned start = ctl->batch_start, cnt = ctl->batch_cnt;
             if (cnt == 0) break;
             const long long t0 = clock64();
-            uint32_t ev[FZ_WPT];  // shared address of each window's eigenvectors (clamped duplicates beyond cnt)
-#pragma unroll
-            for (int b = 0; b < FZ_WPT; ++b) ev[b] = Vq0 + 8 * vsz * ((start + min((unsigned)b, cnt - 1)) % FZ_Q);
-            PeakState<FZ_WPT> ps;
-            ps.reset();
 
-            // Steering-table tiles stream through a FZ_TS-deep TMA ring shared by the scan warps (the
-            // table lives in L2, but under the covariance warps' HBM stream an L2 hit costs > 1000
-            // cycles - far more than one tile of arithmetic).  T counts tiles since kernel start:
-            // slot = T % FZ_TS, tfull parity = (T / FZ_TS) & 1; a tile is released by one arrival per
-            // scan warp on tempty, which the producer (thread 0 of the scan group) awaits before refill.
-            for (int it = 0; it < niter; ++it, ++T) {
-                const int slot = (int)(T % FZ_TS);
-                if (st == 0) {
-                    // keep the ring full: tiles it .. it+FZ_TS-1 of this pass (prologue at it == 0)
-                    for (int a = (it == 0 ? 0 : FZ_TS - 1); a < FZ_TS; ++a) {
-                        const int ia = it + a;
-                        if (ia >= niter) break;
-                        const unsigned Ta = T + a;
-                        const int sa = (int)(Ta % FZ_TS);
-                        if (Ta >= FZ_TS) while (!mbar_try_wait(tb0 + 8 * (FZ_TS + sa), (uint32_t)((Ta / FZ_TS - 1) & 1))) {}
-                        mbar_expect_tx(tb0 + 8 * sa, FZ_TILE_BYTES);
-                        bulk_g2s(tbuf0 + sa * FZ_TILE_BYTES, tbl + (size_t)ia * (FZ_TCOMP * FZ_SCAN_THREADS), FZ_TILE_BYTES, tb0 + 8 * sa);
-                    }
-                }
-                while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
-                const int k = it * FZ_SCAN_THREADS + st;
-                const uint32_t row = tbuf0 + slot * FZ_TILE_BYTES + 8 * st;
-                double ar[M], ai[M], na;
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ar[i]) : "r"(row + 8 * FZ_SCAN_THREADS * (2 * i)));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(ai[i]) : "r"(row + 8 * FZ_SCAN_THREADS * (2 * i + 1)));
-                }
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(na) : "r"(row + 8 * FZ_SCAN_THREADS * 8));
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
-                scan_bin<M, FZ_WPT>(ar, ai, na, k, ev, ps);
+            // B fragments: column n = lane/4 = 2*window + {0: Re row, 1: Im row} of e^H, rows k = t and t + 4 of
+            //   Re column: [ er0, ei0, er1, ei1, er2, ei2, er3, ei3 ]     Im column: [ -ei0, er0, -ei1, er1, ... ]
+            // (c = sum_i conj(e_i) a_i with a row = [Re a0, Im a0, ...]); windows beyond cnt duplicate the last one.
+            uint32_t bh0, bh1, bl0, bl1;
+            {
+                const int wn = min(g >> 1, (int)cnt - 1), im = g & 1;
+                const double *e = Vq + 32 * ((start + wn) % FZ_Q) + 2 * 3 * 4;  // signal vector (largest eigenvalue)
+                auto col = [&](int k) -> float {  // element k of this thread's column
+                    const int i = k >> 1, part = k & 1;  // antenna; 0 -> multiplies Re a_i, 1 -> multiplies Im a_i
+                    const double er = e[2 * i], ei = e[2 * i + 1];
+                    return (float)(im == 0 ? (part == 0 ? er : ei) : (part == 0 ? -ei : er));
+                };
+                const float v0 = col(t), v1 = col(t + 4);
+                bh0 = to_tf32(v0); bl0 = to_tf32(v0 - __uint_as_float(bh0));
+                bh1 = to_tf32(v1); bl1 = to_tf32(v1 - __uint_as_float(bh1));
             }
+
+            // ---- phase 1: minimum of the screen value per window ----
+            float mymin = __int_as_float(0x7f800000);
+            sweep(bh0, bh1, bl0, bl1, [&](int, float d0, float, float d1, float) { mymin = fminf(mymin, fminf(d0, d1)); });
+            mymin = fminf(mymin, __shfl_xor_sync(0xffffffffu, mymin, 4));
+            mymin = fminf(mymin, __shfl_xor_sync(0xffffffffu, mymin, 8));
+            mymin = fminf(mymin, __shfl_xor_sync(0xffffffffu, mymin, 16));
+            if (lane < 4) redmin[swarp * 4 + lane] = mymin;
+            bar_sync_scan();
+            float thr = redmin[t];
 #pragma unroll
-            for (int b = 0; b < FZ_WPT; ++b) {
-                int kk = ps.bestk[b];
-                double P = kk >= 0 ? 1.0 / ps.bestd[b] : 0.0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double Po = __shfl_xor_sync(0xffffffffu, P, o);
-                    const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
-                    if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
+            for (int q = 1; q < FZ_SCAN_WARPS; ++q) thr = fminf(thr, redmin[q * 4 + t]);
+            // candidates: d~ - B||a||^2 <= (min d~ + B max||a||^2) (1 + 2^-10); the relative slack makes every
+            // rejected bin's exact d larger than the best one's by > 2^-11 relative, so its reciprocal is
+            // strictly smaller (no tie can be lost to rounding of 1/d).
+            thr = fmaf(FZ_B, na_max, thr) * 1.0009765625f;
+            const bool mine = (unsigned)t < cnt;  // duplicate columns do not report
+
+            // ---- phase 2: collect the candidates ----
+            sweep(bh0, bh1, bl0, bl1, [&](int row, float d0, float na0, float d1, float na1) {
+                if (mine && fmaf(-FZ_B, na0, d0) <= thr) {
+                    const int s = atomicAdd(&cand_cnt[t], 1);
+                    if (s < FZ_CMAX) cand_bin[t * FZ_CMAX + s] = row;
                 }
-                if (lane == 0) { redP[swarp * FZ_WPT + b] = P; redk[swarp * FZ_WPT + b] = kk; }
+                if (mine && fmaf(-FZ_B, na1, d1) <= thr) {
+                    const int s = atomicAdd(&cand_cnt[t], 1);
+                    if (s < FZ_CMAX) cand_bin[t * FZ_CMAX + s] = row + 8;
+                }
+            });
+            bar_sync_scan();
+
+            // ---- exact fp64 evaluation of the candidates (one thread each) ----
+            const long long te0 = dbg ? clock64() : 0;
+            for (int i = st; i < FZ_WPT * FZ_CMAX; i += FZ_SCAN_THREADS) {
+                const int w = i / FZ_CMAX, j = i % FZ_CMAX;
+                if ((unsigned)w < cnt && j < min(cand_cnt[w], FZ_CMAX))
+                    candP[i] = fused_exact_P(tab_c64, cand_bin[i], Vq0 + 256 * ((start + w) % FZ_Q));
             }
             bar_sync_scan();
-            if ((unsigned)st < cnt) {
-                const int b = st;
-                double P = redP[b];
-                int kk = redk[b];
-                for (int q = 1; q < FZ_SCAN_WARPS; ++q)
-                    if (peak_better(redP[q * FZ_WPT + b], redk[q * FZ_WPT + b], P, kk)) { P = redP[q * FZ_WPT + b]; kk = redk[q * FZ_WPT + b]; }
-                const size_t o = (size_t)qwin[(start + b) % FZ_Q];
+            if ((unsigned)st < cnt && cand_cnt[st] <= FZ_CMAX) {
+                const int w = st, nc = cand_cnt[w];
+                double P = 0.0;
+                int kk = -1;
+                for (int j = 0; j < nc; ++j)
+                    if (peak_better(candP[w * FZ_CMAX + j], cand_bin[w * FZ_CMAX + j], P, kk)) { P = candP[w * FZ_CMAX + j]; kk = cand_bin[w * FZ_CMAX + j]; }
+                const size_t o = (size_t)qwin[(start + w) % FZ_Q];
                 if (kk >= 0) {
                     out.angles[o] = (float)((double)kk * 360.0 / (double)K);  // reference :134, :153
                     if (out.levels) out.levels[o] = (float)P;                 // reference :154
@@ -319,8 +446,44 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl
                     if (out.levels) out.levels[o] = 0.f;
                 }
                 if (out.bins) out.bins[o] = kk;
+                if (dbg) scan_ncand += nc;
             }
-            bar_sync_scan();  // red[] and the queue slots may be reused from here on
+            // ---- fallback: too many candidates (flat spectrum) -> every bin in fp64 ----
+            for (unsigned w = 0; w < cnt; ++w) {
+                if (cand_cnt[w] <= FZ_CMAX) continue;  // uniform over the scan group
+                const uint32_t ev = Vq0 + 256 * ((start + w) % FZ_Q);
+                double P = 0.0;
+                int kk = -1;
+                for (int k = st; k < K; k += FZ_SCAN_THREADS) {
+                    const double p = fused_exact_P(tab_c64, k, ev);
+                    if (p > P) { P = p; kk = k; }  // k ascending per thread: strict '>' keeps the lower bin
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double Po = __shfl_xor_sync(0xffffffffu, P, o);
+                    const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
+                    if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
+                }
+                if (lane == 0) { redP[swarp] = P; redk[swarp] = kk; }
+                bar_sync_scan();
+                if (st == 0) {
+                    for (int q = 1; q < FZ_SCAN_WARPS; ++q)
+                        if (peak_better(redP[q], redk[q], P, kk)) { P = redP[q]; kk = redk[q]; }
+                    const size_t o = (size_t)qwin[(start + w) % FZ_Q];
+                    if (kk >= 0) {
+                        out.angles[o] = (float)((double)kk * 360.0 / (double)K);
+                        if (out.levels) out.levels[o] = (float)P;
+                    } else {
+                        out.angles[o] = 0.f;
+                        if (out.levels) out.levels[o] = 0.f;
+                    }
+                    if (out.bins) out.bins[o] = kk;
+                    ++scan_fallbacks;
+                }
+                bar_sync_scan();
+            }
+            if (dbg) scan_exact += clock64() - te0;
+            bar_sync_scan();  // scratch and the queue slots may be reused from here on
             if (st == 0) {
                 __threadfence_block();
                 ctl->scan_done = start + cnt;
@@ -332,6 +495,9 @@ music4_fused_kernel(const float *__restrict__ in, const double *__restrict__ tbl
             dbg[blockIdx.x * 16 + 11] = clock64() - t_start;
             dbg[blockIdx.x * 16 + 12] = scan_busy;
             dbg[blockIdx.x * 16 + 13] = scan_passes;
+            dbg[blockIdx.x * 16 + 14] = scan_exact;
+            dbg[blockIdx.x * 16 + 15] = scan_fallbacks;
+            dbg[blockIdx.x * 16 + 7] = scan_ncand;
         }
     }
 }
