@@ -6,18 +6,21 @@
 //                window's R is pushed into a 64-slot shared-memory queue (in-order publish).
 //   warp  8      eigensolver: one lane per queued window (up to 32 at once), cyclic Jacobi
 //                (herm_eig_body<4>), eigenvectors written next to the queue slot.
-//   warps 9..15  pseudospectrum scan + peak pick, up to 4 windows per pass:
+//   warps 9..15  pseudospectrum scan + peak pick, up to 8 windows per pass (one sweep of the table):
 //                  1. SCREEN on the tensor cores: c_k = e_s^H a_k for all bins k and the 4 windows as a
 //                     [bins x 8] x [8 x 8] product in 3xTF32 (mma.sync m16n8k8, hi/lo split of both
 //                     operands, fp32 accumulate), d~_k = ||a_k||^2 - |c_k|^2 in fp32.  The FP64 pipe -
 //                     which the covariance warps need - is not touched.
 //                  2. the screen's error is bounded by FZ_B * ||a_k||^2 (derivation below), so only
-//                     bins with d~_k - B||a_k||^2 <= min_k d~_k + B max||a||^2 can hold the fp64
-//                     minimum; they are re-evaluated EXACTLY in fp64 (same complement/direct formula as
+//                     bins whose lower bound d~_k - B||a_k||^2 does not exceed the smallest upper bound
+//                     min_k (d~_k + B||a_k||^2) can hold the fp64 minimum.  Every thread keeps the three
+//                     smallest lower bounds of its own bins (they are interleaved, so a lobe's bins
+//                     spread over threads); after the sweep the survivors are re-evaluated EXACTLY in fp64 (same complement/direct formula as
 //                     the unfused kernels) and the peak is picked among them with the reference's rule
 //                     (strength desc, bin asc, strict '>', /root/reference/lib/baz_music_doa.cc:129-141).
-//                     Typically 2-30 bins per window; if a window has more than FZ_CMAX candidates (flat
-//                     spectra, e.g. an all-zero window) every bin is evaluated in fp64 instead.
+//                     Typically 2-30 bins per window; if a thread's third-smallest bin or more than FZ_CMAX
+//                     bins of a window survive (flat spectra, e.g. an all-zero window) every bin of that
+//                     window is evaluated in fp64 instead.
 //                The result is therefore bit-identical to an all-fp64 scan.
 //
 // Screen error bound.  a is stored in fp32 exactly (the block's table IS complex64); e is rounded
@@ -40,7 +43,8 @@ constexpr int FZ_THREADS = 32 * (FZ_COV_WARPS + 1 + FZ_SCAN_WARPS);  // 512
 constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224
 constexpr int FZ_BINS = 224;    // table rows per TMA tile = 14 MMA tiles of 16 rows, 2 per scan warp
 constexpr int FZ_Q = 64;        // window queue slots per CTA
-constexpr int FZ_WPT = 4;       // windows per scan pass (the 8 MMA columns = 4 windows x {re, im})
+constexpr int FZ_WPT = 8;       // windows per scan pass = 2 column groups of 4 windows x {re, im} (8 MMA columns each)
+constexpr int FZ_TOP = 3;       // smallest lower bounds kept per thread and window
 constexpr int FZ_STAGES = 4;    // 4 KiB TMA stages per covariance warp
 constexpr int FZ_TS = 3;        // steering-table tile stages (TMA ring shared by the scan warps)
 constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * 1024 + FZ_BINS * 4;  // 14 fragment tiles + fp32 ||a||^2 = 15232
@@ -60,18 +64,21 @@ struct FusedCtl {               // shared-memory control block
 constexpr size_t FZ_OFF_TBAR = 512;     // uint64 tfull[FZ_TS], tempty[FZ_TS]
 constexpr size_t FZ_OFF_CTL = 1024;
 constexpr size_t FZ_OFF_WIN = 1088;     // int qwin[FZ_Q]
-constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][4]
-constexpr size_t FZ_OFF_CCNT = 1472;    // int cand_cnt[4]
-constexpr size_t FZ_OFF_CBIN = 1536;    // int cand_bin[4][FZ_CMAX]
-constexpr size_t FZ_OFF_CP = 2048;      // double candP[4][FZ_CMAX]
-constexpr size_t FZ_OFF_RED = 3072;     // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
-constexpr size_t FZ_OFF_RQ = 4096;                            // double Rq[FZ_Q][32]
+constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][FZ_WPT]
+constexpr size_t FZ_OFF_CCNT = 1568;    // int cand_cnt[FZ_WPT]
+constexpr size_t FZ_OFF_CBIN = 1664;    // int cand_bin[FZ_WPT][FZ_CMAX]
+constexpr size_t FZ_OFF_CP = 2688;      // double candP[FZ_WPT][FZ_CMAX]
+constexpr size_t FZ_OFF_RED = 4736;     // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
+constexpr size_t FZ_OFF_RQ = 5120;                            // double Rq[FZ_Q][32]
 constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
 constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256; // FZ_TS table tiles
 constexpr size_t FZ_OFF_RING = (FZ_OFF_TBL + (size_t)FZ_TS * FZ_TILE_BYTES + 127) / 128 * 128;
 constexpr size_t FZ_SMEM = FZ_OFF_RING + (size_t)FZ_COV_WARPS * FZ_STAGES * COV_CHUNK;
 static_assert(FZ_COV_WARPS * FZ_STAGES * 8 <= FZ_OFF_TBAR, "covariance barriers overlap the table barriers");
-static_assert(FZ_OFF_CBIN + 4 * 4 * FZ_CMAX <= FZ_OFF_CP && FZ_OFF_CP + 8 * 4 * FZ_CMAX <= FZ_OFF_RED, "scan scratch layout");
+static_assert(FZ_OFF_RMIN + 4 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_CCNT && FZ_OFF_CCNT + 4 * FZ_WPT <= FZ_OFF_CBIN &&
+                  FZ_OFF_CBIN + 4 * FZ_WPT * FZ_CMAX <= FZ_OFF_CP && FZ_OFF_CP + 8 * FZ_WPT * FZ_CMAX <= FZ_OFF_RED &&
+                  FZ_OFF_RED + 12 * FZ_SCAN_WARPS <= FZ_OFF_RQ,
+              "scan scratch layout");
 static_assert(FZ_SMEM <= 227 * 1024, "fused kernel shared memory");
 static_assert(FZ_TILE_BYTES % 16 == 0, "bulk copy size");
 
@@ -309,11 +316,73 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
         unsigned T = 0;  // table tiles consumed so far (identical in every scan thread)
         long long scan_busy = 0, scan_passes = 0, scan_exact = 0, scan_fallbacks = 0, scan_ncand = 0;
 
-        // One sweep over the whole table through the TMA ring; f(row_g, d~_g, na_g, d~_g8, na_g8) per thread
-        // and MMA tile.  T counts tiles since kernel start: slot = T % FZ_TS, tfull parity =
-        // (T / FZ_TS) & 1; a tile is released by one arrival per scan warp on tempty, which the
-        // producer (thread 0 of the scan group) awaits before refilling the slot.
-        auto sweep = [&](const uint32_t bh0, const uint32_t bh1, const uint32_t bl0, const uint32_t bl1, auto &&f) {
+        for (;;) {
+            if (st == 0) {
+                // A pass streams the whole table from L2 once, so it waits for FZ_WPT windows unless the
+                // covariance and eigensolver stages have drained (then it takes what is left).
+                unsigned start, cnt;
+                for (;;) {
+                    start = ctl->scan_done;
+                    const unsigned avail = ctl->eig_done - start;
+                    if (avail >= (unsigned)FZ_WPT) { cnt = FZ_WPT; break; }
+                    const bool drained = ctl->cov_finished == (unsigned)FZ_COV_WARPS && ctl->cov_pub == ctl->eig_done;
+                    if (drained) { cnt = ctl->eig_done - start; break; }  // may be 0: all done
+                    __nanosleep(200);
+                }
+                ctl->batch_start = start;
+                ctl->batch_cnt = cnt;
+                __threadfence_block();
+            }
+            if (st < FZ_WPT) cand_cnt[st] = 0;
+            bar_sync_scan();
+            const unsigned start = ctl->batch_start, cnt = ctl->batch_cnt;
+            if (cnt == 0) break;
+            const long long t0 = clock64();
+
+            // B fragments per column group gi (windows 4*gi .. 4*gi+3): column n = lane/4 = 2*(window%4) + {0: Re
+            // row, 1: Im row} of e^H, rows k = t and t + 4 of
+            //   Re column: [ er0, ei0, er1, ei1, er2, ei2, er3, ei3 ]     Im column: [ -ei0, er0, -ei1, er1, ... ]
+            // (c = sum_i conj(e_i) a_i with a row = [Re a0, Im a0, ...]); windows beyond cnt duplicate the last one.
+            uint32_t bh0[2], bh1[2], bl0[2], bl1[2];
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const int wn = min(4 * gi + (g >> 1), (int)cnt - 1), im = g & 1;
+                const double *e = Vq + 32 * ((start + wn) % FZ_Q) + 2 * 3 * 4;  // signal vector (largest eigenvalue)
+                auto col = [&](int k) -> float {  // element k of this thread's column
+                    const int i = k >> 1, part = k & 1;  // antenna; 0 -> multiplies Re a_i, 1 -> multiplies Im a_i
+                    const double er = e[2 * i], ei = e[2 * i + 1];
+                    return (float)(im == 0 ? (part == 0 ? er : ei) : (part == 0 ? -ei : er));
+                };
+                const float v0 = col(t), v1 = col(t + 4);
+                bh0[gi] = to_tf32(v0); bl0[gi] = to_tf32(v0 - __uint_as_float(bh0[gi]));
+                bh1[gi] = to_tf32(v1); bl1[gi] = to_tf32(v1 - __uint_as_float(bh1[gi]));
+            }
+            // this thread's windows: 4*gi + t.  Per window: smallest upper bound seen, and the FZ_TOP smallest
+            // lower bounds with their bins (ascending).
+            const float INF = __int_as_float(0x7f800000);
+            float umin[2] = {INF, INF};
+            float lbv[2][FZ_TOP];
+            int lbk[2][FZ_TOP];
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+                for (int j = 0; j < FZ_TOP; ++j) { lbv[gi][j] = INF; lbk[gi][j] = -1; }
+            auto note = [&](const int gi, const int row, const float d, const float na) {
+                const float lb = fmaf(-FZ_B, na, d), ub = fmaf(FZ_B, na, d);
+                umin[gi] = fminf(umin[gi], ub);
+                if (lb < lbv[gi][FZ_TOP - 1]) {  // sorted insert (NaN and the +inf padding never enter)
+                    if (lb < lbv[gi][1]) {
+                        lbv[gi][2] = lbv[gi][1]; lbk[gi][2] = lbk[gi][1];
+                        if (lb < lbv[gi][0]) { lbv[gi][1] = lbv[gi][0]; lbk[gi][1] = lbk[gi][0]; lbv[gi][0] = lb; lbk[gi][0] = row; }
+                        else { lbv[gi][1] = lb; lbk[gi][1] = row; }
+                    } else { lbv[gi][2] = lb; lbk[gi][2] = row; }
+                }
+            };
+
+            // ---- one sweep over the table through the TMA ring ----
+            // T counts tiles since kernel start: slot = T % FZ_TS, tfull parity = (T / FZ_TS) & 1; a tile is
+            // released by one arrival per scan warp on tempty, which the producer (thread 0 of the scan
+            // group) awaits before refilling the slot.
             for (int it = 0; it < ntile; ++it, ++T) {
                 const int slot = (int)(T % FZ_TS);
                 if (st == 0) {
@@ -338,96 +407,64 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                     float na0, na1;
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na0) : "r"(tile + (FZ_BINS / 16) * 1024 + 4 * (mt * 16 + g)));
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na1) : "r"(tile + (FZ_BINS / 16) * 1024 + 4 * (mt * 16 + g + 8)));
-                    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-                    // small terms first: a_lo*e_hi, a_hi*e_lo, then a_hi*e_hi
-                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]), "r"(bh0), "r"(bh1));
-                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bl0), "r"(bl1));
-                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bh0), "r"(bh1));
-                    // (c0, c1) = (Re, Im) of e^H a for row g, window t; (c2, c3) the same for row g + 8
-                    const float d0 = na0 - fmaf(c0, c0, c1 * c1);
-                    const float d1 = na1 - fmaf(c2, c2, c3 * c3);
-                    f(it * FZ_BINS + mt * 16 + g, d0, na0, d1, na1);
+                    const int row = it * FZ_BINS + mt * 16 + g;
+#pragma unroll
+                    for (int gi = 0; gi < 2; ++gi) {
+                        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                        // small terms first: a_lo*e_hi, a_hi*e_lo, then a_hi*e_hi
+                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]), "r"(bh0[gi]), "r"(bh1[gi]));
+                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bl0[gi]), "r"(bl1[gi]));
+                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bh0[gi]), "r"(bh1[gi]));
+                        // (c0, c1) = (Re, Im) of e^H a for row g, window 4*gi + t; (c2, c3) the same for row g + 8
+                        note(gi, row, na0 - fmaf(c0, c0, c1 * c1), na0);
+                        note(gi, row + 8, na1 - fmaf(c2, c2, c3 * c3), na1);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
             }
-        };
 
-        for (;;) {
-            if (st == 0) {
-                unsigned start, cnt;
-                for (;;) {
-                    start = ctl->scan_done;
-                    const unsigned avail = ctl->eig_done - start;
-                    if (avail > 0) { cnt = min(avail, (unsigned)FZ_WPT); break; }
-                    if (ctl->cov_finished == (unsigned)FZ_COV_WARPS && ctl->cov_pub == start) { cnt = 0; break; }
-                    __nanosleep(200);
-                }
-                ctl->batch_start = start;
-                ctl->batch_cnt = cnt;
-                __threadfence_block();
-            }
-            if (st < 4) cand_cnt[st] = 0;
-            bar_sync_scan();
-            const unsigned start = ctl->batch_start, cnt = ctl->batch_cnt;
-            if (cnt == 0) break;
-            const long long t0 = clock64();
-
-            // B fragments: column n = lane/4 = 2*window + {0: Re row, 1: Im row} of e^H, rows k = t and t + 4 of
-            //   Re column: [ er0, ei0, er1, ei1, er2, ei2, er3, ei3 ]     Im column: [ -ei0, er0, -ei1, er1, ... ]
-            // (c = sum_i conj(e_i) a_i with a row = [Re a0, Im a0, ...]); windows beyond cnt duplicate the last one.
-            uint32_t bh0, bh1, bl0, bl1;
-            {
-                const int wn = min(g >> 1, (int)cnt - 1), im = g & 1;
-                const double *e = Vq + 32 * ((start + wn) % FZ_Q) + 2 * 3 * 4;  // signal vector (largest eigenvalue)
-                auto col = [&](int k) -> float {  // element k of this thread's column
-                    const int i = k >> 1, part = k & 1;  // antenna; 0 -> multiplies Re a_i, 1 -> multiplies Im a_i
-                    const double er = e[2 * i], ei = e[2 * i + 1];
-                    return (float)(im == 0 ? (part == 0 ? er : ei) : (part == 0 ? -ei : er));
-                };
-                const float v0 = col(t), v1 = col(t + 4);
-                bh0 = to_tf32(v0); bl0 = to_tf32(v0 - __uint_as_float(bh0));
-                bh1 = to_tf32(v1); bl1 = to_tf32(v1 - __uint_as_float(bh1));
-            }
-
-            // ---- phase 1: minimum of the screen value per window ----
-            float mymin = __int_as_float(0x7f800000);
-            sweep(bh0, bh1, bl0, bl1, [&](int, float d0, float, float d1, float) { mymin = fminf(mymin, fminf(d0, d1)); });
-            mymin = fminf(mymin, __shfl_xor_sync(0xffffffffu, mymin, 4));
-            mymin = fminf(mymin, __shfl_xor_sync(0xffffffffu, mymin, 8));
-            mymin = fminf(mymin, __shfl_xor_sync(0xffffffffu, mymin, 16));
-            if (lane < 4) redmin[swarp * 4 + lane] = mymin;
-            bar_sync_scan();
-            float thr = redmin[t];
+            // ---- smallest upper bound per window over the scan group ----
 #pragma unroll
-            for (int q = 1; q < FZ_SCAN_WARPS; ++q) thr = fminf(thr, redmin[q * 4 + t]);
-            // candidates: d~ - B||a||^2 <= (min d~ + B max||a||^2) (1 + 2^-10); the relative slack makes every
-            // rejected bin's exact d larger than the best one's by > 2^-11 relative, so its reciprocal is
-            // strictly smaller (no tie can be lost to rounding of 1/d).
-            thr = fmaf(FZ_B, na_max, thr) * 1.0009765625f;
-            const bool mine = (unsigned)t < cnt;  // duplicate columns do not report
-
-            // ---- phase 2: collect the candidates ----
-            sweep(bh0, bh1, bl0, bl1, [&](int row, float d0, float na0, float d1, float na1) {
-                if (mine && fmaf(-FZ_B, na0, d0) <= thr) {
-                    const int s = atomicAdd(&cand_cnt[t], 1);
-                    if (s < FZ_CMAX) cand_bin[t * FZ_CMAX + s] = row;
+            for (int gi = 0; gi < 2; ++gi) {
+                float u = umin[gi];
+                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 4));
+                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 8));
+                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 16));
+                if (lane < 4) redmin[swarp * FZ_WPT + 4 * gi + lane] = u;
+            }
+            bar_sync_scan();
+            // candidates: lower bound <= U (1 + 2^-10), U = smallest upper bound; the relative slack makes every
+            // rejected bin's exact d larger than the best one's by > 2^-11 relative, so its reciprocal is strictly
+            // smaller (no tie can be lost to the rounding of 1/d).
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const int w = 4 * gi + t;
+                float thr = redmin[w];
+#pragma unroll
+                for (int q = 1; q < FZ_SCAN_WARPS; ++q) thr = fminf(thr, redmin[q * FZ_WPT + w]);
+                thr = fmaf(fabsf(thr), 0.0009765625f, thr);
+                if ((unsigned)w < cnt) {  // duplicate columns do not report
+#pragma unroll
+                    for (int j = 0; j < FZ_TOP; ++j) {
+                        if (lbv[gi][j] <= thr) {
+                            // the third-smallest surviving means more of this thread's bins might: force the fallback
+                            const int s = atomicAdd(&cand_cnt[w], j == FZ_TOP - 1 ? FZ_CMAX + 1 : 1);
+                            if (s < FZ_CMAX) cand_bin[w * FZ_CMAX + s] = lbk[gi][j];
+                        }
+                    }
                 }
-                if (mine && fmaf(-FZ_B, na1, d1) <= thr) {
-                    const int s = atomicAdd(&cand_cnt[t], 1);
-                    if (s < FZ_CMAX) cand_bin[t * FZ_CMAX + s] = row + 8;
-                }
-            });
+            }
             bar_sync_scan();
 
             // ---- exact fp64 evaluation of the candidates (one thread each) ----
             const long long te0 = dbg ? clock64() : 0;
             for (int i = st; i < FZ_WPT * FZ_CMAX; i += FZ_SCAN_THREADS) {
                 const int w = i / FZ_CMAX, j = i % FZ_CMAX;
-                if ((unsigned)w < cnt && j < min(cand_cnt[w], FZ_CMAX))
+                if ((unsigned)w < cnt && cand_cnt[w] <= FZ_CMAX && j < cand_cnt[w])
                     candP[i] = fused_exact_P(tab_c64, cand_bin[i], Vq0 + 256 * ((start + w) % FZ_Q));
             }
             bar_sync_scan();
