@@ -23,12 +23,14 @@
 //                     window is evaluated in fp64 instead.
 //                The result is therefore bit-identical to an all-fp64 scan.
 //
-// Screen error bound.  a is stored in fp32 exactly (the block's table IS complex64); e is rounded
-// to fp32 (2^-24).  x = x_hi + x_lo + r with x_hi = tf32(x), x_lo = tf32(x - x_hi), |r| <= 2^-22|x|.
-// The three products hi*hi, hi*lo, lo*hi are exact in fp32 (11-bit x 11-bit significands); the
-// dropped lo*lo term is <= 2^-22 |a||e|.  With <= 24 fp32 accumulations (<= 2^-23 each, truncation
-// allowed), |c~ - c| <= 2^-19 sum|a_i||e_i| <= 2^-19 ||a||.  Then ||c~|^2 - |c|^2| <= 2^-18 ||a||^2 (+ 2^-22
-// for the fp32 squares and the subtraction from fl32(||a||^2)).  FZ_B = 2^-16 leaves a 3.5x margin.
+// Screen error bound.  a is stored in fp32 exactly (the block's table IS complex64) and split at run
+// time by truncation: a_hi = a & ~0x1fff (|a - a_hi| < 2^-10|a|), a_lo = (a - a_hi) & ~0x1fff (the
+// subtraction is exact), residual < 2^-20|a|.  e is rounded to fp32 (2^-24) and split with cvt.rna
+// (residual <= 2^-22|e|).  The three products hi*hi, hi*lo, lo*hi are exact in fp32 (11-bit x 11-bit
+// significands); the dropped lo*lo term is <= 2^-21|a||e|.  Allowing every one of the <= 24 fp32
+// accumulations a full 2^-23 (truncating adder), |c~ - c| <= (2^-18.4 + 2^-19.2) sum|a_i||e_i| <= 2^-17.8||a||,
+// hence ||c~|^2 - |c|^2| <= 2^-16.8||a||^2, plus 2^-22 for the fp32 squares and the subtraction from
+// fl32(||a||^2).  FZ_B = 2^-15 leaves > 3x margin over this (already pessimistic) bound.
 //
 // Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does per
 // window except the optional spectrum port).
@@ -44,12 +46,13 @@ constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224
 constexpr int FZ_BINS = 224;    // table rows per TMA tile = 14 MMA tiles of 16 rows, 2 per scan warp
 constexpr int FZ_Q = 64;        // window queue slots per CTA
 constexpr int FZ_WPT = 8;       // windows per scan pass = 2 column groups of 4 windows x {re, im} (8 MMA columns each)
-constexpr int FZ_TOP = 3;       // smallest lower bounds kept per thread and window
+constexpr int FZ_TOP = 5;       // smallest lower bounds kept per thread and window
 constexpr int FZ_STAGES = 4;    // 4 KiB TMA stages per covariance warp
-constexpr int FZ_TS = 3;        // steering-table tile stages (TMA ring shared by the scan warps)
-constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * 1024 + FZ_BINS * 4;  // 14 fragment tiles + fp32 ||a||^2 = 15232
-constexpr int FZ_CMAX = 32;     // exact candidates kept per window before falling back to a full fp64 scan
-constexpr float FZ_B = 1.52587890625e-05f;  // 2^-16, see "Screen error bound"
+constexpr int FZ_TS = 6;        // steering-table tile stages (TMA ring shared by the scan warps)
+constexpr int FZ_FRAG_BYTES = 512;  // one 16 x 8 fp32 A tile in fragment order (16 B per lane)
+constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * FZ_FRAG_BYTES + FZ_BINS * 4;  // 14 fragment tiles + fp32 ||a||^2 = 8064
+constexpr int FZ_CMAX = 128;    // exact candidates kept per window before falling back to a full fp64 scan
+constexpr float FZ_B = 3.0517578125e-05f;  // 2^-15, see "Screen error bound"
 
 struct FusedCtl {               // shared-memory control block
     unsigned cov_seq;           // tickets handed to covariance warps
@@ -67,9 +70,9 @@ constexpr size_t FZ_OFF_WIN = 1088;     // int qwin[FZ_Q]
 constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][FZ_WPT]
 constexpr size_t FZ_OFF_CCNT = 1568;    // int cand_cnt[FZ_WPT]
 constexpr size_t FZ_OFF_CBIN = 1664;    // int cand_bin[FZ_WPT][FZ_CMAX]
-constexpr size_t FZ_OFF_CP = 2688;      // double candP[FZ_WPT][FZ_CMAX]
-constexpr size_t FZ_OFF_RED = 4736;     // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
-constexpr size_t FZ_OFF_RQ = 5120;                            // double Rq[FZ_Q][32]
+constexpr size_t FZ_OFF_CP = 5760;      // double candP[FZ_WPT][FZ_CMAX]
+constexpr size_t FZ_OFF_RED = 13952;    // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
+constexpr size_t FZ_OFF_RQ = 14080;                           // double Rq[FZ_Q][32]
 constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
 constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256; // FZ_TS table tiles
 constexpr size_t FZ_OFF_RING = (FZ_OFF_TBL + (size_t)FZ_TS * FZ_TILE_BYTES + 127) / 128 * 128;
@@ -96,7 +99,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x)
 
 // Steering table in the tensor-core screen's layout.  Per 224-row tile: 14 MMA A-fragment tiles
 // (16 rows x 8 columns; the complex64 row [Re a0, Im a0, .., Re a3, Im a3] IS the A row), stored in
-// fragment order - lane l holds {hi a0..a3, lo a0..a3} with a0 = A[g][t], a1 = A[g+8][t],
+// fragment order - lane l holds {a0..a3} (fp32, split into tf32 hi/lo at run time) with a0 = A[g][t], a1 = A[g+8][t],
 // a2 = A[g][t+4], a3 = A[g+8][t+4], g = l/4, t = l%4 - followed by fl32(||a||^2) per row
 // (+inf for padding rows, which therefore never win).  na_max = max ||a||^2 over the K real rows.
 __global__ void prep_table_tc_kernel(const float *__restrict__ tab, unsigned char *__restrict__ tbl, float *__restrict__ na_max,
@@ -108,16 +111,12 @@ __global__ void prep_table_tc_kernel(const float *__restrict__ tab, unsigned cha
     if (tile16 >= ntile16) return;
     const int g = lane >> 2, t = lane & 3;
     unsigned char *tile = tbl + (size_t)(tile16 / (FZ_BINS / 16)) * FZ_TILE_BYTES;
-    float *frag = reinterpret_cast<float *>(tile) + (size_t)(tile16 % (FZ_BINS / 16)) * 256 + lane * 8;
+    float *frag = reinterpret_cast<float *>(tile) + (size_t)(tile16 % (FZ_BINS / 16)) * (FZ_FRAG_BYTES / 4) + lane * 4;
     const int rows[4] = {g, g + 8, g, g + 8};
     const int cols[4] = {t, t, t + 4, t + 4};
     for (int i = 0; i < 4; ++i) {
         const int bin = tile16 * 16 + rows[i];
-        const float v = bin < K ? tab[(size_t)bin * 8 + cols[i]] : 0.f;
-        const float hi = __uint_as_float(to_tf32(v));
-        const float lo = __uint_as_float(to_tf32(v - hi));
-        frag[i] = hi;
-        frag[4 + i] = lo;
+        frag[i] = bin < K ? tab[(size_t)bin * 8 + cols[i]] : 0.f;
     }
     if (lane < 16) {  // ||a||^2 of row `lane` of this 16-row tile, same fma order as prep_table_kernel
         const int bin = tile16 * 16 + lane;
@@ -127,7 +126,7 @@ __global__ void prep_table_tc_kernel(const float *__restrict__ tab, unsigned cha
             if (bin < K) { re = tab[(size_t)bin * 8 + 2 * i]; im = tab[(size_t)bin * 8 + 2 * i + 1]; }
             na = fma(re, re, fma(im, im, na));
         }
-        float *na32 = reinterpret_cast<float *>(tile + (FZ_BINS / 16) * 1024) + (tile16 % (FZ_BINS / 16)) * 16 + lane;
+        float *na32 = reinterpret_cast<float *>(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES) + (tile16 % (FZ_BINS / 16)) * 16 + lane;
         if (bin < K) {
             const float f = (float)na;
             *na32 = f;
@@ -371,11 +370,16 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 const float lb = fmaf(-FZ_B, na, d), ub = fmaf(FZ_B, na, d);
                 umin[gi] = fminf(umin[gi], ub);
                 if (lb < lbv[gi][FZ_TOP - 1]) {  // sorted insert (NaN and the +inf padding never enter)
-                    if (lb < lbv[gi][1]) {
-                        lbv[gi][2] = lbv[gi][1]; lbk[gi][2] = lbk[gi][1];
-                        if (lb < lbv[gi][0]) { lbv[gi][1] = lbv[gi][0]; lbk[gi][1] = lbk[gi][0]; lbv[gi][0] = lb; lbk[gi][0] = row; }
-                        else { lbv[gi][1] = lb; lbk[gi][1] = row; }
-                    } else { lbv[gi][2] = lb; lbk[gi][2] = row; }
+                    float v = lb;
+                    int kk = row;
+#pragma unroll
+                    for (int j = 0; j < FZ_TOP; ++j) {
+                        const bool sw = v < lbv[gi][j];
+                        const float tv = lbv[gi][j];
+                        const int tk = lbk[gi][j];
+                        lbv[gi][j] = sw ? v : tv;  lbk[gi][j] = sw ? kk : tk;
+                        v = sw ? tv : v;           kk = sw ? tk : kk;
+                    }
                 }
             };
 
@@ -400,13 +404,17 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
-                    const int mt = swarp * 2 + m;  // MMA tile within the 224-row tile
-                    uint32_t ah[4], al[4];
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ah[0]), "=r"(ah[1]), "=r"(ah[2]), "=r"(ah[3]) : "r"(tile + mt * 1024 + lane * 32));
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(tile + mt * 1024 + lane * 32 + 16));
+                    const int mt = m * FZ_SCAN_WARPS + swarp;  // MMA tile within the 224-row tile (round-robin over warps)
+                    uint32_t av[4], ah[4], al[4];
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(av[0]), "=r"(av[1]), "=r"(av[2]), "=r"(av[3]) : "r"(tile + mt * FZ_FRAG_BYTES + lane * 16));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {  // truncating tf32 split on the ALU pipe: a = hi + lo + r, |r| < 2^-20|a|
+                        ah[i] = av[i] & 0xffffe000u;
+                        al[i] = __float_as_uint(__uint_as_float(av[i]) - __uint_as_float(ah[i])) & 0xffffe000u;
+                    }
                     float na0, na1;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na0) : "r"(tile + (FZ_BINS / 16) * 1024 + 4 * (mt * 16 + g)));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na1) : "r"(tile + (FZ_BINS / 16) * 1024 + 4 * (mt * 16 + g + 8)));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na0) : "r"(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES + 4 * (mt * 16 + g)));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na1) : "r"(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES + 4 * (mt * 16 + g + 8)));
                     const int row = it * FZ_BINS + mt * 16 + g;
 #pragma unroll
                     for (int gi = 0; gi < 2; ++gi) {
