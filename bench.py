@@ -40,7 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from gr_baz_b200 import synth  # noqa: E402
+from gr_baz_b200 import sharding, synth  # noqa: E402
 from gr_baz_b200.music_doa_helper import calculate_antenna_array_response  # noqa: E402
 
 
@@ -250,7 +250,7 @@ def run_ours(args):
     # this rank's shard of the global stream: windows w = i*G + rank  (round-robin)
     blk = music_doa(cfg["m"], n, cfg["nsamples"], resp, K, device=local)
     d_in = torch.empty((W, cfg["nsamples"] * 2), dtype=torch.float32, device=dev)
-    widx = np.arange(W, dtype=np.int64) * G + rank
+    widx = sharding.shard_indices(W * G, G, rank)  # round-robin: this rank's windows i*G + rank
     synth.gen_windows_torch(cfg, seed, 0, W, dev, out=d_in, indices=widx)
     d_ang = torch.empty((W, n), dtype=torch.float32, device=dev)
     d_lvl = torch.empty((W, n), dtype=torch.float32, device=dev)
