@@ -6,21 +6,19 @@
 //                window's R is pushed into a 64-slot shared-memory queue (in-order publish).
 //   warp  8      eigensolver: one lane per queued window (up to 32 at once), cyclic Jacobi
 //                (herm_eig_body<4>), eigenvectors written next to the queue slot.
-//   warps 9..15  pseudospectrum scan + peak pick, up to 8 windows per pass (one sweep of the table):
+//   warps 9..15  pseudospectrum scan + peak pick, up to 8 windows per pass (two sweeps of the table):
 //                  1. SCREEN on the tensor cores: c_k = e_s^H a_k for all bins k and the 4 windows as a
 //                     [bins x 8] x [8 x 8] product in 3xTF32 (mma.sync m16n8k8, hi/lo split of both
 //                     operands, fp32 accumulate), d~_k = ||a_k||^2 - |c_k|^2 in fp32.  The FP64 pipe -
 //                     which the covariance warps need - is not touched.
 //                  2. the screen's error is bounded by FZ_B * ||a_k||^2 (derivation below), so only
 //                     bins whose lower bound d~_k - B||a_k||^2 does not exceed the smallest upper bound
-//                     min_k (d~_k + B||a_k||^2) can hold the fp64 minimum.  Every thread keeps the three
-//                     smallest lower bounds of its own bins (they are interleaved, so a lobe's bins
-//                     spread over threads); after the sweep the survivors are re-evaluated EXACTLY in fp64 (same complement/direct formula as
+//                     U = min_k (d~_k + B||a_k||^2) can hold the fp64 minimum: a first sweep finds U, a second
+//                     one lists the survivors, which are re-evaluated EXACTLY in fp64 (same complement/direct formula as
 //                     the unfused kernels) and the peak is picked among them with the reference's rule
 //                     (strength desc, bin asc, strict '>', /root/reference/lib/baz_music_doa.cc:129-141).
-//                     Typically 2-30 bins per window; if a thread's third-smallest bin or more than FZ_CMAX
-//                     bins of a window survive (flat spectra, e.g. an all-zero window) every bin of that
-//                     window is evaluated in fp64 instead.
+//                     Typically 2-60 bins per window; if more than FZ_CMAX bins of a window survive (flat
+//                     spectra, e.g. an all-zero window) every bin of that window is evaluated in fp64 instead.
 //                The result is therefore bit-identical to an all-fp64 scan.
 //
 // Screen error bound.  a is stored in fp32 exactly (the block's table IS complex64) and split at run
@@ -46,7 +44,6 @@ constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224
 constexpr int FZ_BINS = 224;    // table rows per TMA tile = 14 MMA tiles of 16 rows, 2 per scan warp
 constexpr int FZ_Q = 64;        // window queue slots per CTA
 constexpr int FZ_WPT = 8;       // windows per scan pass = 2 column groups of 4 windows x {re, im} (8 MMA columns each)
-constexpr int FZ_TOP = 5;       // smallest lower bounds kept per thread and window
 constexpr int FZ_STAGES = 4;    // 4 KiB TMA stages per covariance warp
 constexpr int FZ_TS = 6;        // steering-table tile stages (TMA ring shared by the scan warps)
 constexpr int FZ_FRAG_BYTES = 512;  // one 16 x 8 fp32 A tile in fragment order (16 B per lane)
@@ -356,86 +353,87 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 bh0[gi] = to_tf32(v0); bl0[gi] = to_tf32(v0 - __uint_as_float(bh0[gi]));
                 bh1[gi] = to_tf32(v1); bl1[gi] = to_tf32(v1 - __uint_as_float(bh1[gi]));
             }
-            // this thread's windows: 4*gi + t.  Per window: smallest upper bound seen, and the FZ_TOP smallest
-            // lower bounds with their bins (ascending).
-            const float INF = __int_as_float(0x7f800000);
-            float umin[2] = {INF, INF};
-            float lbv[2][FZ_TOP];
-            int lbk[2][FZ_TOP];
+            // One sweep over the table through the TMA ring; f(gi, row, d~, ||a||^2) for this thread's two rows
+            // (g, g + 8) of every MMA tile it owns and both column groups (its windows are 4*gi + t).
+            // T counts tiles since kernel start: slot = T % FZ_TS, tfull parity = (T / FZ_TS) & 1; a tile is
+            // released by one arrival per scan warp on tempty, which the producer (thread 0 of the scan
+            // group) awaits before refilling the slot.
+            auto sweep = [&](auto &&f) {
+                for (int it = 0; it < ntile; ++it, ++T) {
+                    const int slot = (int)(T % FZ_TS);
+                    if (st == 0) {
+                        for (int a = (it == 0 ? 0 : FZ_TS - 1); a < FZ_TS; ++a) {
+                            const int ia = it + a;
+                            if (ia >= ntile) break;
+                            const unsigned Ta = T + a;
+                            const int sa = (int)(Ta % FZ_TS);
+                            if (Ta >= FZ_TS) while (!mbar_try_wait(tb0 + 8 * (FZ_TS + sa), (uint32_t)((Ta / FZ_TS - 1) & 1))) {}
+                            mbar_expect_tx(tb0 + 8 * sa, FZ_TILE_BYTES);
+                            bulk_g2s(tbuf0 + sa * FZ_TILE_BYTES, tbl + (size_t)ia * FZ_TILE_BYTES, FZ_TILE_BYTES, tb0 + 8 * sa);
+                        }
+                    }
+                    while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
+                    const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
+                    // both MMA tiles of this warp: loads and the truncating tf32 split (ALU pipe) first
+                    uint32_t ah[2][4], al[2][4];
+                    float na0[2], na1[2];
 #pragma unroll
-            for (int gi = 0; gi < 2; ++gi)
+                    for (int m = 0; m < 2; ++m) {
+                        const int mt = m * FZ_SCAN_WARPS + swarp;  // MMA tile within the 224-row tile (round-robin over warps)
+                        uint32_t av[4];
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(av[0]), "=r"(av[1]), "=r"(av[2]), "=r"(av[3]) : "r"(tile + mt * FZ_FRAG_BYTES + lane * 16));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na0[m]) : "r"(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES + 4 * (mt * 16 + g)));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na1[m]) : "r"(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES + 4 * (mt * 16 + g + 8)));
 #pragma unroll
-                for (int j = 0; j < FZ_TOP; ++j) { lbv[gi][j] = INF; lbk[gi][j] = -1; }
-            auto note = [&](const int gi, const int row, const float d, const float na) {
-                const float lb = fmaf(-FZ_B, na, d), ub = fmaf(FZ_B, na, d);
-                umin[gi] = fminf(umin[gi], ub);
-                if (lb < lbv[gi][FZ_TOP - 1]) {  // sorted insert (NaN and the +inf padding never enter)
-                    float v = lb;
-                    int kk = row;
+                        for (int i = 0; i < 4; ++i) {  // a = hi + lo + r, |r| < 2^-20|a|
+                            ah[m][i] = av[i] & 0xffffe000u;
+                            al[m][i] = __float_as_uint(__uint_as_float(av[i]) - __uint_as_float(ah[m][i])) & 0xffffe000u;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
+                    // 12 independent MMAs (2 tiles x 2 column groups x {a_lo e_hi + a_hi e_lo, a_hi e_hi}); the small
+                    // terms share one accumulator, the big term has its own, so no chain is longer than 2
+                    float cs[2][2][4], cb[2][2][4];
 #pragma unroll
-                    for (int j = 0; j < FZ_TOP; ++j) {
-                        const bool sw = v < lbv[gi][j];
-                        const float tv = lbv[gi][j];
-                        const int tk = lbk[gi][j];
-                        lbv[gi][j] = sw ? v : tv;  lbk[gi][j] = sw ? kk : tk;
-                        v = sw ? tv : v;           kk = sw ? tk : kk;
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) { cs[m][gi][i] = 0.f; cb[m][gi][i] = 0.f; }
+                            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                : "+f"(cb[m][gi][0]), "+f"(cb[m][gi][1]), "+f"(cb[m][gi][2]), "+f"(cb[m][gi][3])
+                                : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
+                            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                : "+f"(cs[m][gi][0]), "+f"(cs[m][gi][1]), "+f"(cs[m][gi][2]), "+f"(cs[m][gi][3])
+                                : "r"(al[m][0]), "r"(al[m][1]), "r"(al[m][2]), "r"(al[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
+                        }
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi)
+                            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                : "+f"(cs[m][gi][0]), "+f"(cs[m][gi][1]), "+f"(cs[m][gi][2]), "+f"(cs[m][gi][3])
+                                : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bl0[gi]), "r"(bl1[gi]));
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                        const int row = it * FZ_BINS + (m * FZ_SCAN_WARPS + swarp) * 16 + g;
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi) {
+                            // (c0, c1) = (Re, Im) of e^H a for row g, window 4*gi + t; (c2, c3) the same for row g + 8
+                            const float c0 = cb[m][gi][0] + cs[m][gi][0], c1 = cb[m][gi][1] + cs[m][gi][1];
+                            const float c2 = cb[m][gi][2] + cs[m][gi][2], c3 = cb[m][gi][3] + cs[m][gi][3];
+                            f(gi, row, na0[m] - fmaf(c0, c0, c1 * c1), na0[m]);
+                            f(gi, row + 8, na1[m] - fmaf(c2, c2, c3 * c3), na1[m]);
+                        }
                     }
                 }
             };
 
-            // ---- one sweep over the table through the TMA ring ----
-            // T counts tiles since kernel start: slot = T % FZ_TS, tfull parity = (T / FZ_TS) & 1; a tile is
-            // released by one arrival per scan warp on tempty, which the producer (thread 0 of the scan
-            // group) awaits before refilling the slot.
-            for (int it = 0; it < ntile; ++it, ++T) {
-                const int slot = (int)(T % FZ_TS);
-                if (st == 0) {
-                    for (int a = (it == 0 ? 0 : FZ_TS - 1); a < FZ_TS; ++a) {
-                        const int ia = it + a;
-                        if (ia >= ntile) break;
-                        const unsigned Ta = T + a;
-                        const int sa = (int)(Ta % FZ_TS);
-                        if (Ta >= FZ_TS) while (!mbar_try_wait(tb0 + 8 * (FZ_TS + sa), (uint32_t)((Ta / FZ_TS - 1) & 1))) {}
-                        mbar_expect_tx(tb0 + 8 * sa, FZ_TILE_BYTES);
-                        bulk_g2s(tbuf0 + sa * FZ_TILE_BYTES, tbl + (size_t)ia * FZ_TILE_BYTES, FZ_TILE_BYTES, tb0 + 8 * sa);
-                    }
-                }
-                while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
-                const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    const int mt = m * FZ_SCAN_WARPS + swarp;  // MMA tile within the 224-row tile (round-robin over warps)
-                    uint32_t av[4], ah[4], al[4];
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(av[0]), "=r"(av[1]), "=r"(av[2]), "=r"(av[3]) : "r"(tile + mt * FZ_FRAG_BYTES + lane * 16));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {  // truncating tf32 split on the ALU pipe: a = hi + lo + r, |r| < 2^-20|a|
-                        ah[i] = av[i] & 0xffffe000u;
-                        al[i] = __float_as_uint(__uint_as_float(av[i]) - __uint_as_float(ah[i])) & 0xffffe000u;
-                    }
-                    float na0, na1;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na0) : "r"(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES + 4 * (mt * 16 + g)));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(na1) : "r"(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES + 4 * (mt * 16 + g + 8)));
-                    const int row = it * FZ_BINS + mt * 16 + g;
-#pragma unroll
-                    for (int gi = 0; gi < 2; ++gi) {
-                        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-                        // small terms first: a_lo*e_hi, a_hi*e_lo, then a_hi*e_hi
-                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(al[0]), "r"(al[1]), "r"(al[2]), "r"(al[3]), "r"(bh0[gi]), "r"(bh1[gi]));
-                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bl0[gi]), "r"(bl1[gi]));
-                        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(ah[0]), "r"(ah[1]), "r"(ah[2]), "r"(ah[3]), "r"(bh0[gi]), "r"(bh1[gi]));
-                        // (c0, c1) = (Re, Im) of e^H a for row g, window 4*gi + t; (c2, c3) the same for row g + 8
-                        note(gi, row, na0 - fmaf(c0, c0, c1 * c1), na0);
-                        note(gi, row + 8, na1 - fmaf(c2, c2, c3 * c3), na1);
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
-            }
-
-            // ---- smallest upper bound per window over the scan group ----
+            // ---- sweep 1: smallest upper bound U = min_k (d~ + B||a||^2) per window ----
+            const float INF = __int_as_float(0x7f800000);
+            float umin[2] = {INF, INF};
+            sweep([&](const int gi, const int, const float d, const float na) { umin[gi] = fminf(umin[gi], fmaf(FZ_B, na, d)); });
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 float u = umin[gi];
@@ -445,27 +443,26 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 if (lane < 4) redmin[swarp * FZ_WPT + 4 * gi + lane] = u;
             }
             bar_sync_scan();
-            // candidates: lower bound <= U (1 + 2^-10), U = smallest upper bound; the relative slack makes every
-            // rejected bin's exact d larger than the best one's by > 2^-11 relative, so its reciprocal is strictly
-            // smaller (no tie can be lost to the rounding of 1/d).
+            // candidates: lower bound d~ - B||a||^2 <= U (1 + 2^-10); the relative slack makes every rejected bin's
+            // exact d larger than the best one's by > 2^-11 relative, so its reciprocal is strictly smaller (no tie
+            // can be lost to the rounding of 1/d).  Columns that duplicate a window (beyond cnt) do not report.
+            float thr[2];
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 const int w = 4 * gi + t;
-                float thr = redmin[w];
+                float u = redmin[w];
 #pragma unroll
-                for (int q = 1; q < FZ_SCAN_WARPS; ++q) thr = fminf(thr, redmin[q * FZ_WPT + w]);
-                thr = fmaf(fabsf(thr), 0.0009765625f, thr);
-                if ((unsigned)w < cnt) {  // duplicate columns do not report
-#pragma unroll
-                    for (int j = 0; j < FZ_TOP; ++j) {
-                        if (lbv[gi][j] <= thr) {
-                            // the third-smallest surviving means more of this thread's bins might: force the fallback
-                            const int s = atomicAdd(&cand_cnt[w], j == FZ_TOP - 1 ? FZ_CMAX + 1 : 1);
-                            if (s < FZ_CMAX) cand_bin[w * FZ_CMAX + s] = lbk[gi][j];
-                        }
-                    }
-                }
+                for (int q = 1; q < FZ_SCAN_WARPS; ++q) u = fminf(u, redmin[q * FZ_WPT + w]);
+                thr[gi] = (unsigned)w < cnt ? fmaf(fabsf(u), 0.0009765625f, u) : -INF;
             }
+
+            // ---- sweep 2: collect the candidates ----
+            sweep([&](const int gi, const int row, const float d, const float na) {
+                if (fmaf(-FZ_B, na, d) <= thr[gi]) {
+                    const int s = atomicAdd(&cand_cnt[4 * gi + t], 1);
+                    if (s < FZ_CMAX) cand_bin[(4 * gi + t) * FZ_CMAX + s] = row;
+                }
+            });
             bar_sync_scan();
 
             // ---- exact fp64 evaluation of the candidates (one thread each) ----
