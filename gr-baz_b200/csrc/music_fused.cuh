@@ -45,10 +45,10 @@ constexpr int FZ_BINS = 224;    // table rows per TMA tile = 14 MMA tiles of 16 
 constexpr int FZ_Q = 64;        // window queue slots per CTA
 constexpr int FZ_WPT = 8;       // windows per scan pass = 2 column groups of 4 windows x {re, im} (8 MMA columns each)
 constexpr int FZ_STAGES = 4;    // 4 KiB TMA stages per covariance warp
-constexpr int FZ_TS = 6;        // steering-table tile stages (TMA ring shared by the scan warps)
+constexpr int FZ_TS = 6;        // steering-table tile stages (cp.async ring shared by the scan warps)
 constexpr int FZ_FRAG_BYTES = 512;  // one 16 x 8 fp32 A tile in fragment order (16 B per lane)
 constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * FZ_FRAG_BYTES + FZ_BINS * 4;  // 14 fragment tiles + fp32 ||a||^2 = 8064
-constexpr int FZ_CMAX = 128;    // exact candidates kept per window before falling back to a full fp64 scan
+constexpr int FZ_CMAX = 256;    // exact candidates kept per window before falling back to a full fp64 scan
 constexpr float FZ_B = 3.0517578125e-05f;  // 2^-15, see "Screen error bound"
 
 struct FusedCtl {               // shared-memory control block
@@ -67,20 +67,18 @@ constexpr size_t FZ_OFF_WIN = 1088;     // int qwin[FZ_Q]
 constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][FZ_WPT]
 constexpr size_t FZ_OFF_CCNT = 1568;    // int cand_cnt[FZ_WPT]
 constexpr size_t FZ_OFF_CBIN = 1664;    // int cand_bin[FZ_WPT][FZ_CMAX]
-constexpr size_t FZ_OFF_CP = 5760;      // double candP[FZ_WPT][FZ_CMAX]
-constexpr size_t FZ_OFF_RED = 13952;    // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
-constexpr size_t FZ_OFF_RQ = 14080;                           // double Rq[FZ_Q][32]
+constexpr size_t FZ_OFF_RED = 9856;     // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
+constexpr size_t FZ_OFF_RQ = 9984;                            // double Rq[FZ_Q][32]
 constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
 constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256; // FZ_TS table tiles
 constexpr size_t FZ_OFF_RING = (FZ_OFF_TBL + (size_t)FZ_TS * FZ_TILE_BYTES + 127) / 128 * 128;
 constexpr size_t FZ_SMEM = FZ_OFF_RING + (size_t)FZ_COV_WARPS * FZ_STAGES * COV_CHUNK;
 static_assert(FZ_COV_WARPS * FZ_STAGES * 8 <= FZ_OFF_TBAR, "covariance barriers overlap the table barriers");
 static_assert(FZ_OFF_RMIN + 4 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_CCNT && FZ_OFF_CCNT + 4 * FZ_WPT <= FZ_OFF_CBIN &&
-                  FZ_OFF_CBIN + 4 * FZ_WPT * FZ_CMAX <= FZ_OFF_CP && FZ_OFF_CP + 8 * FZ_WPT * FZ_CMAX <= FZ_OFF_RED &&
-                  FZ_OFF_RED + 12 * FZ_SCAN_WARPS <= FZ_OFF_RQ,
+                  FZ_OFF_CBIN + 4 * FZ_WPT * FZ_CMAX <= FZ_OFF_RED && FZ_OFF_RED + 12 * FZ_SCAN_WARPS <= FZ_OFF_RQ,
               "scan scratch layout");
 static_assert(FZ_SMEM <= 227 * 1024, "fused kernel shared memory");
-static_assert(FZ_TILE_BYTES % 16 == 0, "bulk copy size");
+static_assert(FZ_TILE_BYTES % 16 == 0 && FZ_TILE_BYTES / 16 <= 3 * FZ_SCAN_THREADS, "table tile copy plan");
 
 __device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_SCAN_THREADS) : "memory"); }
 
@@ -169,7 +167,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
         ctl->batch_start = 0; ctl->batch_cnt = 0;
         const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR);
         for (int s = 0; s < FZ_TS; ++s) {
-            mbar_init(tb0 + 8 * s, 1);                          // tfull: one producer arrival + tx bytes
+            mbar_init(tb0 + 8 * s, FZ_SCAN_THREADS);            // tfull: one cp.async-completion arrival per scan thread
             mbar_init(tb0 + 8 * (FZ_TS + s), FZ_SCAN_WARPS);    // tempty: one arrival per scan warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -302,7 +300,6 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
         float *redmin = reinterpret_cast<float *>(fz_smem + FZ_OFF_RMIN);
         int *cand_cnt = reinterpret_cast<int *>(fz_smem + FZ_OFF_CCNT);
         int *cand_bin = reinterpret_cast<int *>(fz_smem + FZ_OFF_CBIN);
-        double *candP = reinterpret_cast<double *>(fz_smem + FZ_OFF_CP);
         double *redP = reinterpret_cast<double *>(fz_smem + FZ_OFF_RED);
         int *redk = reinterpret_cast<int *>(fz_smem + FZ_OFF_RED + 8 * FZ_SCAN_WARPS);
         const uint32_t Vq0 = smem_u32(Vq);
@@ -353,25 +350,33 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 bh0[gi] = to_tf32(v0); bl0[gi] = to_tf32(v0 - __uint_as_float(bh0[gi]));
                 bh1[gi] = to_tf32(v1); bl1[gi] = to_tf32(v1 - __uint_as_float(bh1[gi]));
             }
-            // One sweep over the table through the TMA ring; f(gi, row, d~, ||a||^2) for this thread's two rows
+            // One sweep over the table through the FZ_TS-deep ring; f(gi, row, d~, ||a||^2) for this thread's two rows
             // (g, g + 8) of every MMA tile it owns and both column groups (its windows are 4*gi + t).
             // T counts tiles since kernel start: slot = T % FZ_TS, tfull parity = (T / FZ_TS) & 1; a tile is
-            // released by one arrival per scan warp on tempty, which the producer (thread 0 of the scan
-            // group) awaits before refilling the slot.
+            // released by one arrival per scan warp on tempty.
+            // Table tiles arrive by cp.async (LDGSTS, 16 B per request through the LSU): the SM's TMA queue is FIFO
+            // and permanently holds ~100 KB of HBM-bound covariance requests, behind which an L2-resident
+            // table tile would wait for thousands of cycles.  Every scan thread copies its 2-3 chunks of tile
+            // T + D and its completion arrives on tfull[slot]; a slot is reused once all warps released it.
+            constexpr int D = FZ_TS - 1;  // prefetch distance in tiles
+            auto issue_tile = [&](const int ia, const unsigned Ta) {
+                const int sa = (int)(Ta % FZ_TS);
+                if (Ta >= FZ_TS) while (!mbar_try_wait(tb0 + 8 * (FZ_TS + sa), (uint32_t)((Ta / FZ_TS - 1) & 1))) {}
+                const unsigned char *src = tbl + (size_t)ia * FZ_TILE_BYTES;
+                const uint32_t dst = tbuf0 + sa * FZ_TILE_BYTES;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int chunk = st + c * FZ_SCAN_THREADS;  // 16-byte chunk of the tile
+                    if (chunk < FZ_TILE_BYTES / 16)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * chunk), "l"(src + 16 * chunk) : "memory");
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tb0 + 8 * sa) : "memory");
+            };
             auto sweep = [&](auto &&f) {
+                for (int a = 0; a < D && a < ntile; ++a) issue_tile(a, T + a);
                 for (int it = 0; it < ntile; ++it, ++T) {
                     const int slot = (int)(T % FZ_TS);
-                    if (st == 0) {
-                        for (int a = (it == 0 ? 0 : FZ_TS - 1); a < FZ_TS; ++a) {
-                            const int ia = it + a;
-                            if (ia >= ntile) break;
-                            const unsigned Ta = T + a;
-                            const int sa = (int)(Ta % FZ_TS);
-                            if (Ta >= FZ_TS) while (!mbar_try_wait(tb0 + 8 * (FZ_TS + sa), (uint32_t)((Ta / FZ_TS - 1) & 1))) {}
-                            mbar_expect_tx(tb0 + 8 * sa, FZ_TILE_BYTES);
-                            bulk_g2s(tbuf0 + sa * FZ_TILE_BYTES, tbl + (size_t)ia * FZ_TILE_BYTES, FZ_TILE_BYTES, tb0 + 8 * sa);
-                        }
-                    }
+                    if (it + D < ntile) issue_tile(it + D, T + D);
                     while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
                     const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
                     // both MMA tiles of this warp: loads and the truncating tf32 split (ALU pipe) first
@@ -465,30 +470,37 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             });
             bar_sync_scan();
 
-            // ---- exact fp64 evaluation of the candidates (one thread each) ----
+            // ---- exact fp64 evaluation: one warp per window, lanes over its candidates ----
             const long long te0 = dbg ? clock64() : 0;
-            for (int i = st; i < FZ_WPT * FZ_CMAX; i += FZ_SCAN_THREADS) {
-                const int w = i / FZ_CMAX, j = i % FZ_CMAX;
-                if ((unsigned)w < cnt && cand_cnt[w] <= FZ_CMAX && j < cand_cnt[w])
-                    candP[i] = fused_exact_P(tab_c64, cand_bin[i], Vq0 + 256 * ((start + w) % FZ_Q));
-            }
-            bar_sync_scan();
-            if ((unsigned)st < cnt && cand_cnt[st] <= FZ_CMAX) {
-                const int w = st, nc = cand_cnt[w];
+            for (unsigned w = swarp; w < cnt; w += FZ_SCAN_WARPS) {
+                const int nc = cand_cnt[w];
+                if (nc > FZ_CMAX) continue;  // handled by the whole scan group below
+                const uint32_t ev = Vq0 + 256 * ((start + w) % FZ_Q);
                 double P = 0.0;
                 int kk = -1;
-                for (int j = 0; j < nc; ++j)
-                    if (peak_better(candP[w * FZ_CMAX + j], cand_bin[w * FZ_CMAX + j], P, kk)) { P = candP[w * FZ_CMAX + j]; kk = cand_bin[w * FZ_CMAX + j]; }
-                const size_t o = (size_t)qwin[(start + w) % FZ_Q];
-                if (kk >= 0) {
-                    out.angles[o] = (float)((double)kk * 360.0 / (double)K);  // reference :134, :153
-                    if (out.levels) out.levels[o] = (float)P;                 // reference :154
-                } else {
-                    out.angles[o] = 0.f;                                      // (0,0) initial pair, reference :95
-                    if (out.levels) out.levels[o] = 0.f;
+                for (int j = lane; j < nc; j += 32) {
+                    const int k = cand_bin[w * FZ_CMAX + j];
+                    const double p = fused_exact_P(tab_c64, k, ev);
+                    if (peak_better(p, k, P, kk)) { P = p; kk = k; }  // list order is arbitrary: full comparator
                 }
-                if (out.bins) out.bins[o] = kk;
-                if (dbg) scan_ncand += nc;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double Po = __shfl_xor_sync(0xffffffffu, P, o);
+                    const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
+                    if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
+                }
+                if (lane == 0) {
+                    const size_t o = (size_t)qwin[(start + w) % FZ_Q];
+                    if (kk >= 0) {
+                        out.angles[o] = (float)((double)kk * 360.0 / (double)K);  // reference :134, :153
+                        if (out.levels) out.levels[o] = (float)P;                 // reference :154
+                    } else {
+                        out.angles[o] = 0.f;                                      // (0,0) initial pair, reference :95
+                        if (out.levels) out.levels[o] = 0.f;
+                    }
+                    if (out.bins) out.bins[o] = kk;
+                    if (dbg) scan_ncand += nc;
+                }
             }
             // ---- fallback: too many candidates (flat spectrum) -> every bin in fp64 ----
             for (unsigned w = 0; w < cnt; ++w) {
