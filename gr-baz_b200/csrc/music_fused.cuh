@@ -261,7 +261,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         }
         if (lane == 0) atomicAdd((unsigned *)&ctl->cov_finished, 1u);
-        if (dbg && lane == 0 && warp < 7) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;
+        if (dbg && lane == 0 && warp < 4) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0;
@@ -308,6 +308,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
         const float na_max = __ldg(na_max_p);
         unsigned T = 0;  // table tiles consumed so far (identical in every scan thread)
         long long scan_busy = 0, scan_passes = 0, scan_exact = 0, scan_fallbacks = 0, scan_ncand = 0;
+        long long tr_issue = 0, tr_full = 0, tr_comp = 0;
 
         for (;;) {
             if (st == 0) {
@@ -376,8 +377,11 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 for (int a = 0; a < D && a < ntile; ++a) issue_tile(a, T + a);
                 for (int it = 0; it < ntile; ++it, ++T) {
                     const int slot = (int)(T % FZ_TS);
+                    const long long tk0 = dbg ? clock64() : 0;
                     if (it + D < ntile) issue_tile(it + D, T + D);
+                    const long long tk1 = dbg ? clock64() : 0;
                     while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
+                    const long long tk2 = dbg ? clock64() : 0;
                     const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
                     // both MMA tiles of this warp: loads and the truncating tf32 split (ALU pipe) first
                     uint32_t ah[2][4], al[2][4];
@@ -397,41 +401,42 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
-                    // 12 independent MMAs (2 tiles x 2 column groups x {a_lo e_hi + a_hi e_lo, a_hi e_hi}); the small
-                    // terms share one accumulator, the big term has its own, so no chain is longer than 2
-                    float cs[2][2][4], cb[2][2][4];
+                    // 12 MMAs = 3 (a_lo e_hi, a_hi e_lo, a_hi e_hi; small terms first) for each of the 4 (tile, column
+                    // group) accumulators, issued round-robin so that dependent MMAs are 4 instructions (~32
+                    // cycles at one HMMA.1688 per 8 cycles) apart - more than the ~20-cycle MMA latency.
+                    float c[2][2][4];
 #pragma unroll
                     for (int m = 0; m < 2; ++m)
 #pragma unroll
-                        for (int gi = 0; gi < 2; ++gi) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) { cs[m][gi][i] = 0.f; cb[m][gi][i] = 0.f; }
-                            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                : "+f"(cb[m][gi][0]), "+f"(cb[m][gi][1]), "+f"(cb[m][gi][2]), "+f"(cb[m][gi][3])
-                                : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
-                            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                : "+f"(cs[m][gi][0]), "+f"(cs[m][gi][1]), "+f"(cs[m][gi][2]), "+f"(cs[m][gi][3])
-                                : "r"(al[m][0]), "r"(al[m][1]), "r"(al[m][2]), "r"(al[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
-                        }
+                        for (int gi = 0; gi < 2; ++gi)
+                            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                                : "=f"(c[m][gi][0]), "=f"(c[m][gi][1]), "=f"(c[m][gi][2]), "=f"(c[m][gi][3])
+                                : "r"(al[m][0]), "r"(al[m][1]), "r"(al[m][2]), "r"(al[m][3]), "r"(bh0[gi]), "r"(bh1[gi]), "f"(0.f));
 #pragma unroll
                     for (int m = 0; m < 2; ++m)
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi)
                             asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                : "+f"(cs[m][gi][0]), "+f"(cs[m][gi][1]), "+f"(cs[m][gi][2]), "+f"(cs[m][gi][3])
+                                : "+f"(c[m][gi][0]), "+f"(c[m][gi][1]), "+f"(c[m][gi][2]), "+f"(c[m][gi][3])
                                 : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bl0[gi]), "r"(bl1[gi]));
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int gi = 0; gi < 2; ++gi)
+                            asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                : "+f"(c[m][gi][0]), "+f"(c[m][gi][1]), "+f"(c[m][gi][2]), "+f"(c[m][gi][3])
+                                : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
 #pragma unroll
                     for (int m = 0; m < 2; ++m) {
                         const int row = it * FZ_BINS + (m * FZ_SCAN_WARPS + swarp) * 16 + g;
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi) {
                             // (c0, c1) = (Re, Im) of e^H a for row g, window 4*gi + t; (c2, c3) the same for row g + 8
-                            const float c0 = cb[m][gi][0] + cs[m][gi][0], c1 = cb[m][gi][1] + cs[m][gi][1];
-                            const float c2 = cb[m][gi][2] + cs[m][gi][2], c3 = cb[m][gi][3] + cs[m][gi][3];
-                            f(gi, row, na0[m] - fmaf(c0, c0, c1 * c1), na0[m]);
-                            f(gi, row + 8, na1[m] - fmaf(c2, c2, c3 * c3), na1[m]);
+                            f(gi, row, na0[m] - fmaf(c[m][gi][0], c[m][gi][0], c[m][gi][1] * c[m][gi][1]), na0[m]);
+                            f(gi, row + 8, na1[m] - fmaf(c[m][gi][2], c[m][gi][2], c[m][gi][3] * c[m][gi][3]), na1[m]);
                         }
                     }
+                    if (dbg) { const long long tk3 = clock64(); tr_issue += tk1 - tk0; tr_full += tk2 - tk1; tr_comp += tk3 - tk2; }
                 }
             };
 
@@ -552,6 +557,9 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             dbg[blockIdx.x * 16 + 14] = scan_exact;
             dbg[blockIdx.x * 16 + 15] = scan_fallbacks;
             dbg[blockIdx.x * 16 + 7] = scan_ncand;
+            dbg[blockIdx.x * 16 + 4] = tr_issue;  // (overwrite covariance warps 4..6 slots)
+            dbg[blockIdx.x * 16 + 5] = tr_full;
+            dbg[blockIdx.x * 16 + 6] = tr_comp;
         }
     }
 }

@@ -130,6 +130,29 @@ __global__ void k_mix_alu(double *out, int seed, double b, long long *cyc)
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// legacy mma.sync TF32 m16n8k8 (SASS HMMA.1688.F32.TF32): CH independent accumulators per warp
+template <int CH>
+__global__ void k_hmma_tf32(float *out, long long *cyc)
+{
+    float c[CH][4];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) { c[i][0] = threadIdx.x; c[i][1] = i; c[i][2] = 1.f; c[i][3] = 2.f; }
+    unsigned a0 = 0x3f800000u + threadIdx.x * 8192u, a1 = a0 + 8192u, a2 = a0 + 16384u, a3 = a0 + 24576u, b0 = 0x3f000000u, b1 = 0x3f002000u;
+    long long t0 = clock64();
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+    long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 __global__ void k_dmma(double *out, double a, double b, long long *cyc)
 {
     double c[4][2];
@@ -185,6 +208,11 @@ int main()
     run("DFMA 2 chains, 1 warp/SMSP", [&](int g, int t) { k_dfma_chains<2><<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, 128, 1, sms, cyc);
     run("DFMA 4 chains, 1 warp/SMSP", [&](int g, int t) { k_dfma_chains<4><<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, 128, 1, sms, cyc);
     run("DFMA 8 chains, 1 warp/SMSP", [&](int g, int t) { k_dfma_chains<8><<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, 128, 1, sms, cyc);
+    // HMMA.1688.F32.TF32: "lane-ops" here = MMA instructions * 32, so MMAs/clk/SM = value / 32
+    run("HMMA tf32 1 chain 1w/SMSP", [&](int g, int t) { k_hmma_tf32<1><<<g, t>>>((float *)out, cyc); }, 1, 128, 1, sms, cyc);
+    run("HMMA tf32 4 chains 1w/SMSP", [&](int g, int t) { k_hmma_tf32<4><<<g, t>>>((float *)out, cyc); }, 4, 128, 1, sms, cyc);
+    run("HMMA tf32 8 chains 1w/SMSP", [&](int g, int t) { k_hmma_tf32<8><<<g, t>>>((float *)out, cyc); }, 8, 128, 1, sms, cyc);
+    run("HMMA tf32 8 chains 4w/SMSP", [&](int g, int t) { k_hmma_tf32<8><<<g, t>>>((float *)out, cyc); }, 8, 512, 1, sms, cyc);
     for (int tpb : {128, 1024}) {
         run("DFMA", [&](int g, int t) { k_dfma<<<g, t>>>(out, 1.0000001, 1e-9, cyc); }, 8, tpb, 1, sms, cyc);
         run("F2F.F64.F32", [&](int g, int t) { k_f2f<<<g, t>>>(out, 1, cyc); }, 8, tpb, 1, sms, cyc);
