@@ -41,13 +41,15 @@ constexpr int FZ_COV_WARPS = 8;
 constexpr int FZ_SCAN_WARPS = 7;
 constexpr int FZ_THREADS = 32 * (FZ_COV_WARPS + 1 + FZ_SCAN_WARPS);  // 512
 constexpr int FZ_SCAN_THREADS = 32 * FZ_SCAN_WARPS;                  // 224
-constexpr int FZ_BINS = 224;    // table rows per TMA tile = 14 MMA tiles of 16 rows, 2 per scan warp
+constexpr int FZ_MPW = 4;        // MMA tiles (16 rows) per scan warp and table tile: more work per ring iteration
+                                 // amortises the fixed load -> split -> MMA -> reduce latency chain of a warp
+constexpr int FZ_BINS = 16 * FZ_SCAN_WARPS * FZ_MPW;  // table rows per ring tile
 constexpr int FZ_Q = 64;        // window queue slots per CTA
 constexpr int FZ_WPT = 8;       // windows per scan pass = 2 column groups of 4 windows x {re, im} (8 MMA columns each)
 constexpr int FZ_STAGES = 4;    // 4 KiB TMA stages per covariance warp
-constexpr int FZ_TS = 6;        // steering-table tile stages (cp.async ring shared by the scan warps)
+constexpr int FZ_TS = 3;        // steering-table tile stages (cp.async ring shared by the scan warps)
 constexpr int FZ_FRAG_BYTES = 512;  // one 16 x 8 fp32 A tile in fragment order (16 B per lane)
-constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * FZ_FRAG_BYTES + FZ_BINS * 4;  // 14 fragment tiles + fp32 ||a||^2 = 8064
+constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * FZ_FRAG_BYTES + FZ_BINS * 4;  // fragment tiles + fp32 ||a||^2
 constexpr int FZ_CMAX = 256;    // exact candidates kept per window before falling back to a full fp64 scan
 constexpr float FZ_B = 3.0517578125e-05f;  // 2^-15, see "Screen error bound"
 
@@ -78,7 +80,8 @@ static_assert(FZ_OFF_RMIN + 4 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_CCNT && FZ_OFF_
                   FZ_OFF_CBIN + 4 * FZ_WPT * FZ_CMAX <= FZ_OFF_RED && FZ_OFF_RED + 12 * FZ_SCAN_WARPS <= FZ_OFF_RQ,
               "scan scratch layout");
 static_assert(FZ_SMEM <= 227 * 1024, "fused kernel shared memory");
-static_assert(FZ_TILE_BYTES % 16 == 0 && FZ_TILE_BYTES / 16 <= 3 * FZ_SCAN_THREADS, "table tile copy plan");
+constexpr int FZ_CPT = (FZ_TILE_BYTES / 16 + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS;  // 16-byte copies per thread and tile
+static_assert(FZ_TILE_BYTES % 16 == 0, "table tile copy plan");
 
 __device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_SCAN_THREADS) : "memory"); }
 
@@ -366,7 +369,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 const unsigned char *src = tbl + (size_t)ia * FZ_TILE_BYTES;
                 const uint32_t dst = tbuf0 + sa * FZ_TILE_BYTES;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
+                for (int c = 0; c < FZ_CPT; ++c) {
                     const int chunk = st + c * FZ_SCAN_THREADS;  // 16-byte chunk of the tile
                     if (chunk < FZ_TILE_BYTES / 16)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * chunk), "l"(src + 16 * chunk) : "memory");
@@ -384,10 +387,10 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                     const long long tk2 = dbg ? clock64() : 0;
                     const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
                     // both MMA tiles of this warp: loads and the truncating tf32 split (ALU pipe) first
-                    uint32_t ah[2][4], al[2][4];
-                    float na0[2], na1[2];
+                    uint32_t ah[FZ_MPW][4], al[FZ_MPW][4];
+                    float na0[FZ_MPW], na1[FZ_MPW];
 #pragma unroll
-                    for (int m = 0; m < 2; ++m) {
+                    for (int m = 0; m < FZ_MPW; ++m) {
                         const int mt = m * FZ_SCAN_WARPS + swarp;  // MMA tile within the 224-row tile (round-robin over warps)
                         uint32_t av[4];
                         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(av[0]), "=r"(av[1]), "=r"(av[2]), "=r"(av[3]) : "r"(tile + mt * FZ_FRAG_BYTES + lane * 16));
@@ -404,30 +407,30 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                     // 12 MMAs = 3 (a_lo e_hi, a_hi e_lo, a_hi e_hi; small terms first) for each of the 4 (tile, column
                     // group) accumulators, issued round-robin so that dependent MMAs are 4 instructions (~32
                     // cycles at one HMMA.1688 per 8 cycles) apart - more than the ~20-cycle MMA latency.
-                    float c[2][2][4];
+                    float c[FZ_MPW][2][4];
 #pragma unroll
-                    for (int m = 0; m < 2; ++m)
+                    for (int m = 0; m < FZ_MPW; ++m)
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi)
                             asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
                                 : "=f"(c[m][gi][0]), "=f"(c[m][gi][1]), "=f"(c[m][gi][2]), "=f"(c[m][gi][3])
                                 : "r"(al[m][0]), "r"(al[m][1]), "r"(al[m][2]), "r"(al[m][3]), "r"(bh0[gi]), "r"(bh1[gi]), "f"(0.f));
 #pragma unroll
-                    for (int m = 0; m < 2; ++m)
+                    for (int m = 0; m < FZ_MPW; ++m)
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi)
                             asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                 : "+f"(c[m][gi][0]), "+f"(c[m][gi][1]), "+f"(c[m][gi][2]), "+f"(c[m][gi][3])
                                 : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bl0[gi]), "r"(bl1[gi]));
 #pragma unroll
-                    for (int m = 0; m < 2; ++m)
+                    for (int m = 0; m < FZ_MPW; ++m)
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi)
                             asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                 : "+f"(c[m][gi][0]), "+f"(c[m][gi][1]), "+f"(c[m][gi][2]), "+f"(c[m][gi][3])
                                 : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
 #pragma unroll
-                    for (int m = 0; m < 2; ++m) {
+                    for (int m = 0; m < FZ_MPW; ++m) {
                         const int row = it * FZ_BINS + (m * FZ_SCAN_WARPS + swarp) * 16 + g;
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi) {
