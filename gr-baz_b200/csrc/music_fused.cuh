@@ -70,14 +70,16 @@ constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][FZ_WPT]
 constexpr size_t FZ_OFF_CCNT = 1568;    // int cand_cnt[FZ_WPT]
 constexpr size_t FZ_OFF_CBIN = 1664;    // int cand_bin[FZ_WPT][FZ_CMAX]
 constexpr size_t FZ_OFF_RED = 9856;     // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
-constexpr size_t FZ_OFF_RQ = 9984;                            // double Rq[FZ_Q][32]
+constexpr size_t FZ_OFF_BEST = 9984;    // u64 bestP[FZ_WPT]; int bestk[FZ_WPT]; int admitted[FZ_WPT]
+constexpr size_t FZ_OFF_RQ = 10240;                           // double Rq[FZ_Q][32]
 constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
 constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256; // FZ_TS table tiles
 constexpr size_t FZ_OFF_RING = (FZ_OFF_TBL + (size_t)FZ_TS * FZ_TILE_BYTES + 127) / 128 * 128;
 constexpr size_t FZ_SMEM = FZ_OFF_RING + (size_t)FZ_COV_WARPS * FZ_STAGES * COV_CHUNK;
 static_assert(FZ_COV_WARPS * FZ_STAGES * 8 <= FZ_OFF_TBAR, "covariance barriers overlap the table barriers");
 static_assert(FZ_OFF_RMIN + 4 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_CCNT && FZ_OFF_CCNT + 4 * FZ_WPT <= FZ_OFF_CBIN &&
-                  FZ_OFF_CBIN + 4 * FZ_WPT * FZ_CMAX <= FZ_OFF_RED && FZ_OFF_RED + 12 * FZ_SCAN_WARPS <= FZ_OFF_RQ,
+                  FZ_OFF_CBIN + 4 * FZ_WPT * FZ_CMAX <= FZ_OFF_RED && FZ_OFF_RED + 12 * FZ_SCAN_WARPS <= FZ_OFF_BEST &&
+                  FZ_OFF_BEST + 16 * FZ_WPT <= FZ_OFF_RQ,
               "scan scratch layout");
 static_assert(FZ_SMEM <= 227 * 1024, "fused kernel shared memory");
 constexpr int FZ_CPT = (FZ_TILE_BYTES / 16 + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS;  // 16-byte copies per thread and tile
@@ -86,7 +88,10 @@ static_assert(FZ_TILE_BYTES % 16 == 0, "table tile copy plan");
 __device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_SCAN_THREADS) : "memory"); }
 
 __host__ __device__ inline int fused_tiles(int K) { return (K + FZ_BINS - 1) / FZ_BINS; }
-__host__ __device__ inline size_t fused_table_bytes(int K) { return (size_t)fused_tiles(K) * FZ_TILE_BYTES; }
+// Stride of the decimated table (tile 0): every fused_stride(K)-th row, at most FZ_BINS of them.  The first
+// sweep only needs an upper bound of the minimum, and a subsample gives one at 1/fused_tiles(K) of the cost.
+__host__ __device__ inline int fused_stride(int K) { return fused_tiles(K); }
+__host__ __device__ inline size_t fused_table_bytes(int K) { return (size_t)(1 + fused_tiles(K)) * FZ_TILE_BYTES; }
 
 __device__ __forceinline__ uint32_t to_tf32(float x)
 {
@@ -99,32 +104,37 @@ __device__ __forceinline__ uint32_t to_tf32(float x)
 // (16 rows x 8 columns; the complex64 row [Re a0, Im a0, .., Re a3, Im a3] IS the A row), stored in
 // fragment order - lane l holds {a0..a3} (fp32, split into tf32 hi/lo at run time) with a0 = A[g][t], a1 = A[g+8][t],
 // a2 = A[g][t+4], a3 = A[g+8][t+4], g = l/4, t = l%4 - followed by fl32(||a||^2) per row
-// (+inf for padding rows, which therefore never win).  na_max = max ||a||^2 over the K real rows.
+// (+inf for padding rows, which therefore never win).  Tile 0 holds every fused_stride(K)-th row (the
+// subsample of the first sweep), tiles 1.. the whole table.  na_max = max ||a||^2 over the K real rows.
 __global__ void prep_table_tc_kernel(const float *__restrict__ tab, unsigned char *__restrict__ tbl, float *__restrict__ na_max,
                                      int K)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (16-row tile, lane)
-    const int tile16 = idx >> 5, lane = idx & 31;
-    const int ntile16 = fused_tiles(K) * (FZ_BINS / 16);
+    const int tile16 = idx >> 5, lane = idx & 31;           // tile16 < FZ_BINS/16: decimated tile, then the full table
+    const int per = FZ_BINS / 16;
+    const int ntile16 = (1 + fused_tiles(K)) * per;
     if (tile16 >= ntile16) return;
     const int g = lane >> 2, t = lane & 3;
-    unsigned char *tile = tbl + (size_t)(tile16 / (FZ_BINS / 16)) * FZ_TILE_BYTES;
-    float *frag = reinterpret_cast<float *>(tile) + (size_t)(tile16 % (FZ_BINS / 16)) * (FZ_FRAG_BYTES / 4) + lane * 4;
+    const bool dec = tile16 < per;
+    const int stride = dec ? fused_stride(K) : 1;
+    const int row0 = dec ? tile16 * 16 : (tile16 - per) * 16;  // first (sub)sampled row of this 16-row tile
+    unsigned char *tile = tbl + (size_t)(tile16 / per) * FZ_TILE_BYTES;
+    float *frag = reinterpret_cast<float *>(tile) + (size_t)(tile16 % per) * (FZ_FRAG_BYTES / 4) + lane * 4;
     const int rows[4] = {g, g + 8, g, g + 8};
     const int cols[4] = {t, t, t + 4, t + 4};
     for (int i = 0; i < 4; ++i) {
-        const int bin = tile16 * 16 + rows[i];
+        const int bin = (row0 + rows[i]) * stride;
         frag[i] = bin < K ? tab[(size_t)bin * 8 + cols[i]] : 0.f;
     }
     if (lane < 16) {  // ||a||^2 of row `lane` of this 16-row tile, same fma order as prep_table_kernel
-        const int bin = tile16 * 16 + lane;
+        const int bin = (row0 + lane) * stride;
         double na = 0.0;
         for (int i = 0; i < 4; ++i) {
             double re = 0.0, im = 0.0;
             if (bin < K) { re = tab[(size_t)bin * 8 + 2 * i]; im = tab[(size_t)bin * 8 + 2 * i + 1]; }
             na = fma(re, re, fma(im, im, na));
         }
-        float *na32 = reinterpret_cast<float *>(tile + (FZ_BINS / 16) * FZ_FRAG_BYTES) + (tile16 % (FZ_BINS / 16)) * 16 + lane;
+        float *na32 = reinterpret_cast<float *>(tile + per * FZ_FRAG_BYTES) + (tile16 % per) * 16 + lane;
         if (bin < K) {
             const float f = (float)na;
             *na32 = f;
@@ -306,7 +316,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
         double *redP = reinterpret_cast<double *>(fz_smem + FZ_OFF_RED);
         int *redk = reinterpret_cast<int *>(fz_smem + FZ_OFF_RED + 8 * FZ_SCAN_WARPS);
         const uint32_t Vq0 = smem_u32(Vq);
-        const int ntile = fused_tiles(K);
+        const int ntile_full = fused_tiles(K);
         const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR), tbuf0 = smem_u32(fz_smem + FZ_OFF_TBL);
         const float na_max = __ldg(na_max_p);
         unsigned T = 0;  // table tiles consumed so far (identical in every scan thread)
@@ -376,12 +386,12 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tb0 + 8 * sa) : "memory");
             };
-            auto sweep = [&](auto &&f) {
-                for (int a = 0; a < D && a < ntile; ++a) issue_tile(a, T + a);
+            auto sweep = [&](const int tile0, const int ntile, const int rstride, auto &&f) {
+                for (int a = 0; a < D && a < ntile; ++a) issue_tile(tile0 + a, T + a);
                 for (int it = 0; it < ntile; ++it, ++T) {
                     const int slot = (int)(T % FZ_TS);
                     const long long tk0 = dbg ? clock64() : 0;
-                    if (it + D < ntile) issue_tile(it + D, T + D);
+                    if (it + D < ntile) issue_tile(tile0 + it + D, T + D);
                     const long long tk1 = dbg ? clock64() : 0;
                     while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
                     const long long tk2 = dbg ? clock64() : 0;
@@ -431,22 +441,23 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                                 : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
 #pragma unroll
                     for (int m = 0; m < FZ_MPW; ++m) {
-                        const int row = it * FZ_BINS + (m * FZ_SCAN_WARPS + swarp) * 16 + g;
+                        const int row = (it * FZ_BINS + (m * FZ_SCAN_WARPS + swarp) * 16 + g) * rstride;
 #pragma unroll
                         for (int gi = 0; gi < 2; ++gi) {
                             // (c0, c1) = (Re, Im) of e^H a for row g, window 4*gi + t; (c2, c3) the same for row g + 8
                             f(gi, row, na0[m] - fmaf(c[m][gi][0], c[m][gi][0], c[m][gi][1] * c[m][gi][1]), na0[m]);
-                            f(gi, row + 8, na1[m] - fmaf(c[m][gi][2], c[m][gi][2], c[m][gi][3] * c[m][gi][3]), na1[m]);
+                            f(gi, row + 8 * rstride, na1[m] - fmaf(c[m][gi][2], c[m][gi][2], c[m][gi][3] * c[m][gi][3]), na1[m]);
                         }
                     }
                     if (dbg) { const long long tk3 = clock64(); tr_issue += tk1 - tk0; tr_full += tk2 - tk1; tr_comp += tk3 - tk2; }
                 }
             };
 
-            // ---- sweep 1: smallest upper bound U = min_k (d~ + B||a||^2) per window ----
+            // ---- sweep 1 (the decimated tile only): an upper bound U >= min_k d_k per window, U = min over the
+            // subsample of d~ + B||a||^2 (any bin's upper bound bounds the minimum from above) ----
             const float INF = __int_as_float(0x7f800000);
             float umin[2] = {INF, INF};
-            sweep([&](const int gi, const int, const float d, const float na) { umin[gi] = fminf(umin[gi], fmaf(FZ_B, na, d)); });
+            sweep(0, 1, fused_stride(K), [&](const int gi, const int, const float d, const float na) { umin[gi] = fminf(umin[gi], fmaf(FZ_B, na, d)); });
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 float u = umin[gi];
@@ -469,8 +480,8 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 thr[gi] = (unsigned)w < cnt ? fmaf(fabsf(u), 0.0009765625f, u) : -INF;
             }
 
-            // ---- sweep 2: collect the candidates ----
-            sweep([&](const int gi, const int row, const float d, const float na) {
+            // ---- sweep 2 (the whole table): collect the candidates ----
+            sweep(1, ntile_full, 1, [&](const int gi, const int row, const float d, const float na) {
                 if (fmaf(-FZ_B, na, d) <= thr[gi]) {
                     const int s = atomicAdd(&cand_cnt[4 * gi + t], 1);
                     if (s < FZ_CMAX) cand_bin[(4 * gi + t) * FZ_CMAX + s] = row;
@@ -478,41 +489,65 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             });
             bar_sync_scan();
 
-            // ---- exact fp64 evaluation: one warp per window, lanes over its candidates ----
+            // ---- exact fp64 evaluation: the candidates of all windows flattened over the scan threads ----
+            // (strength desc, bin asc) is resolved with two shared-memory atomics per candidate: max over the
+            // fp64 bit pattern of P (positive doubles order like their bits), then min over the bins that hold it.
             const long long te0 = dbg ? clock64() : 0;
-            for (unsigned w = swarp; w < cnt; w += FZ_SCAN_WARPS) {
-                const int nc = cand_cnt[w];
-                if (nc > FZ_CMAX) continue;  // handled by the whole scan group below
-                const uint32_t ev = Vq0 + 256 * ((start + w) % FZ_Q);
-                double P = 0.0;
-                int kk = -1;
-                for (int j = lane; j < nc; j += 32) {
-                    const int k = cand_bin[w * FZ_CMAX + j];
-                    const double p = fused_exact_P(tab_c64, k, ev);
-                    if (peak_better(p, k, P, kk)) { P = p; kk = k; }  // list order is arbitrary: full comparator
-                }
+            unsigned long long *bestP = reinterpret_cast<unsigned long long *>(fz_smem + FZ_OFF_BEST);
+            int *bestk = reinterpret_cast<int *>(fz_smem + FZ_OFF_BEST + 8 * FZ_WPT);
+            int *admitted = reinterpret_cast<int *>(fz_smem + FZ_OFF_BEST + 12 * FZ_WPT);
+            constexpr int IPT = 3;  // candidates per thread kept in registers
+            int pre[FZ_WPT + 1];
+            pre[0] = 0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double Po = __shfl_xor_sync(0xffffffffu, P, o);
-                    const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
-                    if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
-                }
-                if (lane == 0) {
-                    const size_t o = (size_t)qwin[(start + w) % FZ_Q];
-                    if (kk >= 0) {
-                        out.angles[o] = (float)((double)kk * 360.0 / (double)K);  // reference :134, :153
-                        if (out.levels) out.levels[o] = (float)P;                 // reference :154
-                    } else {
-                        out.angles[o] = 0.f;                                      // (0,0) initial pair, reference :95
-                        if (out.levels) out.levels[o] = 0.f;
+            for (int w = 0; w < FZ_WPT; ++w) {
+                const int nc = ((unsigned)w < cnt) ? cand_cnt[w] : 0;
+                const bool ok = nc <= FZ_CMAX && pre[w] + nc <= IPT * FZ_SCAN_THREADS;
+                pre[w + 1] = pre[w] + (ok ? nc : 0);
+                if (st == w) { bestP[w] = 0ull; bestk[w] = 0x7fffffff; admitted[w] = ok ? 1 : 0; }
+            }
+            bar_sync_scan();
+            double myP[IPT];
+            int myk[IPT], myw[IPT];
+#pragma unroll
+            for (int r = 0; r < IPT; ++r) {
+                const int i = st + r * FZ_SCAN_THREADS;
+                myk[r] = -1; myw[r] = 0; myP[r] = 0.0;
+                if (i < pre[FZ_WPT]) {
+                    int w = 0;
+#pragma unroll
+                    for (int q = 1; q < FZ_WPT; ++q) w += (i >= pre[q]) ? 1 : 0;
+                    const int k = cand_bin[w * FZ_CMAX + (i - pre[w])];
+                    const double P = fused_exact_P(tab_c64, k, Vq0 + 256 * ((start + w) % FZ_Q));
+                    if (P > 0.0) {  // NaN and non-positive strengths are never inserted (reference :132)
+                        myP[r] = P; myk[r] = k; myw[r] = w;
+                        atomicMax(&bestP[w], (unsigned long long)__double_as_longlong(P));
                     }
-                    if (out.bins) out.bins[o] = kk;
-                    if (dbg) scan_ncand += nc;
                 }
             }
+            bar_sync_scan();
+#pragma unroll
+            for (int r = 0; r < IPT; ++r)
+                if (myk[r] >= 0 && (unsigned long long)__double_as_longlong(myP[r]) == bestP[myw[r]]) atomicMin(&bestk[myw[r]], myk[r]);
+            bar_sync_scan();
+            if ((unsigned)st < cnt && admitted[st]) {
+                const int w = st;
+                const int kk = bestk[w] == 0x7fffffff ? -1 : bestk[w];
+                const double P = __longlong_as_double((long long)bestP[w]);
+                const size_t o = (size_t)qwin[(start + w) % FZ_Q];
+                if (kk >= 0) {
+                    out.angles[o] = (float)((double)kk * 360.0 / (double)K);  // reference :134, :153
+                    if (out.levels) out.levels[o] = (float)P;                 // reference :154
+                } else {
+                    out.angles[o] = 0.f;                                      // (0,0) initial pair, reference :95
+                    if (out.levels) out.levels[o] = 0.f;
+                }
+                if (out.bins) out.bins[o] = kk;
+            }
+            if (dbg && st == 0) scan_ncand += pre[FZ_WPT];
             // ---- fallback: too many candidates (flat spectrum) -> every bin in fp64 ----
             for (unsigned w = 0; w < cnt; ++w) {
-                if (cand_cnt[w] <= FZ_CMAX) continue;  // uniform over the scan group
+                if (admitted[w]) continue;  // uniform over the scan group
                 const uint32_t ev = Vq0 + 256 * ((start + w) % FZ_Q);
                 double P = 0.0;
                 int kk = -1;
