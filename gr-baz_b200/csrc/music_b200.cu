@@ -62,6 +62,9 @@ struct music_b200 {
     cudaStream_t s_cov = nullptr, s_scan = nullptr;
     cudaEvent_t ev_in = nullptr;
     bool pipeline = false;   // MUSIC_B200_PIPE=1 enables the sub-batch pipeline (launch-bound at 10k windows: off)
+    unsigned *work_ctr = nullptr;      // fused kernel: [0] window tickets, [1] finished CTAs (self-resetting)
+    cudaEvent_t fused_done = nullptr;  // launches of one handle are serialised (they share work_ctr)
+    bool fused_used = false;
     long long *fused_trace = nullptr;  // MUSIC_B200_TRACE=1: per-CTA clock64 trace of the fused kernel (tools/fused_trace.py)
     bool fused = true;       // MUSIC_B200_FUSED=0 forces the three-kernel path
     bool scan_fast = true;   // MUSIC_B200_SCAN=general disables the specialised n == 1 kernel
@@ -300,10 +303,14 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
         const int grid = std::min<int>(h->sm_count, (int)((nwindows + FZ_COV_WARPS - 1) / FZ_COV_WARPS));
+        if (h->fused_used) CU(h, cudaStreamWaitEvent(st, h->fused_done, 0));
         const DeviceTable &tb = h->table[h->cur_table];
         music4_fused_kernel<<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, tb.fz, tb.c64, tb.na_max, (int)nwindows, (int)h->N,
-                                                             (int)h->K, PeakOut{d_ang, d_lvl, d_bins}, h->fused_trace);
+                                                             (int)h->K, PeakOut{d_ang, d_lvl, d_bins}, h->work_ctr,
+                                                             h->fused_trace);
         h->launches++;
+        CU(h, cudaEventRecord(h->fused_done, st));
+        h->fused_used = true;
         if (tev) for (int i = 1; i < 5; ++i) cudaEventRecord(tev[i], st);
         CU(h, cudaGetLastError());
         return MUSIC_B200_OK;
@@ -495,6 +502,9 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         }
         if (const char *e = getenv("MUSIC_B200_SCAN")) h->scan_fast = strcmp(e, "general") != 0;
         if (const char *e = getenv("MUSIC_B200_FUSED")) h->fused = atoi(e) != 0;
+        CU(h, cudaEventCreateWithFlags(&h->fused_done, cudaEventDisableTiming));
+        CU(h, cudaMalloc(&h->work_ctr, 2 * sizeof(unsigned)));
+        CU(h, cudaMemset(h->work_ctr, 0, 2 * sizeof(unsigned)));
         if (getenv("MUSIC_B200_TRACE")) {
             CU(h, cudaMalloc(&h->fused_trace, 16 * sizeof(long long) * 1024));
             CU(h, cudaMemset(h->fused_trace, 0, 16 * sizeof(long long) * 1024));
@@ -607,6 +617,8 @@ void music_b200_destroy(music_b200 *h)
     if (h->s_scan) cudaStreamDestroy(h->s_scan);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->fused_trace);
+    cudaFree(h->work_ctr);
+    if (h->fused_done) cudaEventDestroy(h->fused_done);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->table[i].c64); cudaFree(h->table[i].soa); cudaFree(h->table[i].fz); cudaFree(h->table[i].na_max);
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);

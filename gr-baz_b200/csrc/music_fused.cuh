@@ -64,6 +64,7 @@ struct FusedCtl {               // shared-memory control block
 };
 
 constexpr size_t FZ_OFF_TBAR = 512;     // uint64 tfull[FZ_TS], tempty[FZ_TS]
+constexpr size_t FZ_OFF_WRING = 768;    // int wring[FZ_COV_WARPS][8]: window ids claimed by each covariance warp
 constexpr size_t FZ_OFF_CTL = 1024;
 constexpr size_t FZ_OFF_WIN = 1088;     // int qwin[FZ_Q]
 constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][FZ_WPT]
@@ -165,9 +166,12 @@ __device__ __forceinline__ double fused_exact_P(const float *__restrict__ tab_c6
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restrict__ tbl /* fused_table_bytes(K) */,
                     const float *__restrict__ tab_c64 /* [K][4] complex64 */, const float *__restrict__ na_max_p, int W, int N,
-                    int K, PeakOut out, long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */)
+                    int K, PeakOut out, unsigned *__restrict__ work_ctr /* [0]: window tickets, [1]: finished CTAs; both zero between launches */,
+                    long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */)
 {
     const long long t_start = clock64();
+    unsigned long long g_start = 0;
+    if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
     extern __shared__ __align__(128) unsigned char fz_smem[];
     FusedCtl *ctl = reinterpret_cast<FusedCtl *>(fz_smem + FZ_OFF_CTL);
     int *qwin = reinterpret_cast<int *>(fz_smem + FZ_OFF_WIN);
@@ -193,10 +197,14 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
         uint64_t *bars = reinterpret_cast<uint64_t *>(fz_smem) + warp * FZ_STAGES;
         unsigned char *ring = fz_smem + FZ_OFF_RING + (size_t)warp * FZ_STAGES * COV_CHUNK;
         const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
-        const int gw = blockIdx.x * FZ_COV_WARPS + warp, total_warps = gridDim.x * FZ_COV_WARPS;
+        // Windows are claimed one at a time from a global ticket counter (dynamic balance: 10 000 windows over
+        // 1184 warps would otherwise leave 8 or 9 per warp, i.e. a 12 % longer critical path).  The producer
+        // (lane 0) claims the next window when it requests the last chunk of the current one and hands the id
+        // to the consumer side through a small per-warp ring; -1 ends the stream.
+        volatile int *wring = reinterpret_cast<volatile int *>(fz_smem + FZ_OFF_WRING) + warp * 8;
+        unsigned *ctr = work_ctr;
         const size_t win_bytes = (size_t)N * 32;
         const int cpw = (int)((win_bytes + COV_CHUNK - 1) / COV_CHUNK);
-        const int nwin = gw < W ? (W - gw + total_warps - 1) / total_warps : 0;
         const unsigned char *src0 = reinterpret_cast<const unsigned char *>(in);
         if (lane == 0) {
             for (int s = 0; s < FZ_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
@@ -204,25 +212,37 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncwarp();
-        // producer state (lane 0): next chunk to request = chunk iq of this warp's window number ij
-        int iq = 0, ij = 0, islot = 0;
+        // producer state (lane 0): next chunk to request = chunk iq of window iw (-1: stream exhausted)
+        int iq = 0, iw = -1, islot = 0, wr = 0;
+        auto claim = [&]() {
+            const unsigned tkt = atomicAdd(ctr, 1u);
+            iw = tkt < (unsigned)W ? (int)tkt : -1;
+            wring[wr & 7] = iw;
+            ++wr;
+        };
         auto issue = [&]() {
+            if (iw < 0) return;
             const size_t off = (size_t)iq * COV_CHUNK;
             const uint32_t bytes = (uint32_t)min((size_t)COV_CHUNK, win_bytes - off);
-            const unsigned char *src = src0 + ((size_t)gw + (size_t)ij * total_warps) * win_bytes + off;
+            const unsigned char *src = src0 + (size_t)iw * win_bytes + off;
             mbar_expect_tx(bar0 + 8 * islot, bytes);
             bulk_g2s(ring0 + islot * COV_CHUNK, src, bytes, bar0 + 8 * islot);
-            if (++iq == cpw) { iq = 0; ++ij; }
             if (++islot == FZ_STAGES) islot = 0;
+            if (++iq == cpw) { iq = 0; claim(); }
         };
-        if (lane == 0)
-            for (int s = 0; s < FZ_STAGES && ij < nwin; ++s) issue();
+        if (lane == 0) {
+            claim();
+            for (int s = 0; s < FZ_STAGES; ++s) issue();
+        }
+        __syncwarp();
         double acc[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         int slot = 0;
         uint32_t parity = 0;
-        for (int j = 0; j < nwin; ++j) {
+        for (int rd = 0;; ++rd) {
+            const int wcur = wring[rd & 7];  // written by lane 0 at least one chunk request ago
+            if (wcur < 0) break;
             for (int q = 0; q < cpw; ++q) {
                 while (!mbar_try_wait(bar0 + 8 * slot, parity)) {}
                 const size_t off = (size_t)q * COV_CHUNK;
@@ -241,9 +261,10 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                     for (int s = lane; s < nsnap; s += 32) cov4_accumulate(acc, buf[2 * s], buf[2 * s + 1]);
                 }
                 __syncwarp();  // every lane is done reading the slot -> it may be refilled
-                if (lane == 0 && ij < nwin) issue();
+                if (lane == 0) issue();
                 if (++slot == FZ_STAGES) { slot = 0; parity ^= 1; }
             }
+            __syncwarp();  // makes lane 0's ring writes (claims during this window) visible to the next read
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
             if (lane == 0) {
@@ -265,7 +286,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                         Rw[2 * (b * 4 + a)] = re;  Rw[2 * (b * 4 + a) + 1] = -im;
                         e += 2;
                     }
-                qwin[seq % FZ_Q] = gw + j * total_warps;
+                qwin[seq % FZ_Q] = wcur;
                 while (ctl->cov_pub != seq) {}  // publish in ticket order
                 __threadfence_block();
                 ctl->cov_pub = seq + 1;
@@ -274,7 +295,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         }
         if (lane == 0) atomicAdd((unsigned *)&ctl->cov_finished, 1u);
-        if (dbg && lane == 0 && warp < 4) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;
+        if (dbg && lane == 0 && warp < 2) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0;
@@ -598,6 +619,21 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             dbg[blockIdx.x * 16 + 4] = tr_issue;  // (overwrite covariance warps 4..6 slots)
             dbg[blockIdx.x * 16 + 5] = tr_full;
             dbg[blockIdx.x * 16 + 6] = tr_comp;
+            unsigned long long g_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+            dbg[blockIdx.x * 16 + 3] = (long long)(g_end - g_start);   // ns, this CTA's lifetime (overwrites covariance warp 3's slot)
+            dbg[blockIdx.x * 16 + 2] = (long long)g_start;             // ns, absolute start (overwrites covariance warp 2's slot)
+        }
+    }
+    // The last CTA to finish re-arms the ticket counter for the next launch (launches of one handle are
+    // serialised by the host, and by now every covariance warp has drawn a ticket >= W).
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&work_ctr[1], 1u) == gridDim.x - 1) {
+            work_ctr[0] = 0;
+            work_ctr[1] = 0;
+            __threadfence();
         }
     }
 }
