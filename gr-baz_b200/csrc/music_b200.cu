@@ -122,7 +122,7 @@ int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t s
     prep_table_kernel<<<ntiles, TILE, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.soa, (int)h->K, (int)h->m);
     h->launches++;
     if (t.fz) {
-        const int threads = (1 + fused_tiles((int)h->K)) * (FZ_BINS / 16) * 32;
+        const int threads = (FZ_NDEC + fused_tiles((int)h->K)) * (FZ_BINS / 16) * 32;
         CU(h, cudaMemsetAsync(t.na_max, 0, sizeof(float), st));
         prep_table_tc_kernel<<<(threads + 255) / 256, 256, 0, st>>>(t.c64, t.fz, t.na_max, (int)h->K);
         h->launches++;

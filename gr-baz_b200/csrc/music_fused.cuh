@@ -89,10 +89,12 @@ static_assert(FZ_TILE_BYTES % 16 == 0, "table tile copy plan");
 __device__ __forceinline__ void bar_sync_scan() { asm volatile("bar.sync 1, %0;" ::"n"(FZ_SCAN_THREADS) : "memory"); }
 
 __host__ __device__ inline int fused_tiles(int K) { return (K + FZ_BINS - 1) / FZ_BINS; }
-// Stride of the decimated table (tile 0): every fused_stride(K)-th row, at most FZ_BINS of them.  The first
-// sweep only needs an upper bound of the minimum, and a subsample gives one at 1/fused_tiles(K) of the cost.
-__host__ __device__ inline int fused_stride(int K) { return fused_tiles(K); }
-__host__ __device__ inline size_t fused_table_bytes(int K) { return (size_t)(1 + fused_tiles(K)) * FZ_TILE_BYTES; }
+// Decimated table (tiles 0 .. FZ_NDEC-1): every fused_stride(K)-th row, at most FZ_NDEC * FZ_BINS of them.  The
+// first sweep only needs an upper bound of the minimum; a subsample gives one at a fraction of the cost, and
+// the finer it is the fewer bins survive into the exact evaluation.
+constexpr int FZ_NDEC = 2;
+__host__ __device__ inline int fused_stride(int K) { return (K + FZ_NDEC * FZ_BINS - 1) / (FZ_NDEC * FZ_BINS); }
+__host__ __device__ inline size_t fused_table_bytes(int K) { return (size_t)(FZ_NDEC + fused_tiles(K)) * FZ_TILE_BYTES; }
 
 __device__ __forceinline__ uint32_t to_tf32(float x)
 {
@@ -105,20 +107,20 @@ __device__ __forceinline__ uint32_t to_tf32(float x)
 // (16 rows x 8 columns; the complex64 row [Re a0, Im a0, .., Re a3, Im a3] IS the A row), stored in
 // fragment order - lane l holds {a0..a3} (fp32, split into tf32 hi/lo at run time) with a0 = A[g][t], a1 = A[g+8][t],
 // a2 = A[g][t+4], a3 = A[g+8][t+4], g = l/4, t = l%4 - followed by fl32(||a||^2) per row
-// (+inf for padding rows, which therefore never win).  Tile 0 holds every fused_stride(K)-th row (the
-// subsample of the first sweep), tiles 1.. the whole table.  na_max = max ||a||^2 over the K real rows.
+// (+inf for padding rows, which therefore never win).  Tiles 0..FZ_NDEC-1 hold every fused_stride(K)-th row
+// (the subsample of the first sweep), the following tiles the whole table.  na_max = max ||a||^2 over the K real rows.
 __global__ void prep_table_tc_kernel(const float *__restrict__ tab, unsigned char *__restrict__ tbl, float *__restrict__ na_max,
                                      int K)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (16-row tile, lane)
     const int tile16 = idx >> 5, lane = idx & 31;           // tile16 < FZ_BINS/16: decimated tile, then the full table
     const int per = FZ_BINS / 16;
-    const int ntile16 = (1 + fused_tiles(K)) * per;
+    const int ntile16 = (FZ_NDEC + fused_tiles(K)) * per;
     if (tile16 >= ntile16) return;
     const int g = lane >> 2, t = lane & 3;
-    const bool dec = tile16 < per;
+    const bool dec = tile16 < FZ_NDEC * per;
     const int stride = dec ? fused_stride(K) : 1;
-    const int row0 = dec ? tile16 * 16 : (tile16 - per) * 16;  // first (sub)sampled row of this 16-row tile
+    const int row0 = dec ? tile16 * 16 : (tile16 - FZ_NDEC * per) * 16;  // first (sub)sampled row of this 16-row tile
     unsigned char *tile = tbl + (size_t)(tile16 / per) * FZ_TILE_BYTES;
     float *frag = reinterpret_cast<float *>(tile) + (size_t)(tile16 % per) * (FZ_FRAG_BYTES / 4) + lane * 4;
     const int rows[4] = {g, g + 8, g, g + 8};
@@ -354,7 +356,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                     const unsigned avail = ctl->eig_done - start;
                     if (avail >= (unsigned)FZ_WPT) { cnt = FZ_WPT; break; }
                     const bool drained = ctl->cov_finished == (unsigned)FZ_COV_WARPS && ctl->cov_pub == ctl->eig_done;
-                    if (drained) { cnt = ctl->eig_done - start; break; }  // may be 0: all done
+                    if (drained) { cnt = min(ctl->eig_done - start, (unsigned)FZ_WPT); break; }  // may be 0: all done
                     __nanosleep(200);
                 }
                 ctl->batch_start = start;
@@ -478,7 +480,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             // subsample of d~ + B||a||^2 (any bin's upper bound bounds the minimum from above) ----
             const float INF = __int_as_float(0x7f800000);
             float umin[2] = {INF, INF};
-            sweep(0, 1, fused_stride(K), [&](const int gi, const int, const float d, const float na) { umin[gi] = fminf(umin[gi], fmaf(FZ_B, na, d)); });
+            sweep(0, FZ_NDEC, fused_stride(K), [&](const int gi, const int, const float d, const float na) { umin[gi] = fminf(umin[gi], fmaf(FZ_B, na, d)); });
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 float u = umin[gi];
@@ -502,7 +504,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             }
 
             // ---- sweep 2 (the whole table): collect the candidates ----
-            sweep(1, ntile_full, 1, [&](const int gi, const int row, const float d, const float na) {
+            sweep(FZ_NDEC, ntile_full, 1, [&](const int gi, const int row, const float d, const float na) {
                 if (fmaf(-FZ_B, na, d) <= thr[gi]) {
                     const int s = atomicAdd(&cand_cnt[4 * gi + t], 1);
                     if (s < FZ_CMAX) cand_bin[(4 * gi + t) * FZ_CMAX + s] = row;
@@ -517,7 +519,7 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             unsigned long long *bestP = reinterpret_cast<unsigned long long *>(fz_smem + FZ_OFF_BEST);
             int *bestk = reinterpret_cast<int *>(fz_smem + FZ_OFF_BEST + 8 * FZ_WPT);
             int *admitted = reinterpret_cast<int *>(fz_smem + FZ_OFF_BEST + 12 * FZ_WPT);
-            constexpr int IPT = 3;  // candidates per thread kept in registers
+            constexpr int IPT = 4;  // candidates per thread kept in registers
             int pre[FZ_WPT + 1];
             pre[0] = 0;
 #pragma unroll

@@ -256,3 +256,35 @@ def test_full_size_single_windows_configs_3_and_5():
         ref = co.work_batch(x, cfg["m"], cfg["n"], table)
         got = run_block(cfg, table, x, spectrum=True, device_path=True, want_internals=True)
         assert_parity(got, ref, cfg["n"])
+
+
+def test_fused_kernel_matches_unfused_path_on_every_window(monkeypatch):
+    """Config 2 at full size through both device paths: the fused persistent kernel (tensor-core screen +
+    exact fp64 candidates, dynamic window tickets) must give bit-identical bins AND levels to the unfused
+    all-fp64 kernels for every one of the 10 000 windows, run after run (regression: partial final scan
+    passes once skipped windows), and for a window count that leaves ragged final passes."""
+    cfg = synth.config(2)
+    table = helpers.table_for(cfg)
+    dev = torch.device("cuda:0")
+    W = cfg["windows"]
+    d_in = synth.gen_windows_torch(cfg, synth.BASE_SEED + 2, 0, W, dev)
+
+    def run(fused, nw, reps):
+        monkeypatch.setenv("MUSIC_B200_FUSED", "1" if fused else "0")
+        blk = music_doa(cfg["m"], cfg["n"], cfg["nsamples"], table.tolist(), cfg["resolution"])
+        outs = []
+        for _ in range(reps):
+            a = torch.full((nw, 1), -7.0, dtype=torch.float32, device=dev)
+            l = torch.full((nw, 1), -7.0, dtype=torch.float32, device=dev)
+            b = torch.full((nw, 1), -7, dtype=torch.int32, device=dev)
+            blk.process_device(d_in.data_ptr(), nw, a.data_ptr(), l.data_ptr(), None, b.data_ptr(),
+                               stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            outs.append((a.cpu().numpy(), l.cpu().numpy(), b.cpu().numpy()))
+        blk.close()
+        return outs
+
+    for nw in (W, 1187, 9):
+        ref = run(False, nw, 1)[0]
+        for got in run(True, nw, 3):
+            assert np.array_equal(got[2], ref[2]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
