@@ -245,6 +245,9 @@ int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, float *d_ang
         const int grid = (W + 127) / 128;
         switch (M) {
         case 4: eig_kernel<4, true><<<grid, 128, 0, st>>>(ws.R, ws.ev, ws.Vt, M, (int)W); break;
+        case 8: eig_coop_kernel<8><<<(W + EIGC_WARPS - 1) / EIGC_WARPS, EIGC_WARPS * 32, 0, st>>>(ws.R, ws.ev, ws.Vt, (int)W); break;
+        case 12: eig_coop_kernel<12><<<(W + EIGC_WARPS - 1) / EIGC_WARPS, EIGC_WARPS * 32, 0, st>>>(ws.R, ws.ev, ws.Vt, (int)W); break;
+        case 16: eig_coop_kernel<16><<<(W + EIGC_WARPS - 1) / EIGC_WARPS, EIGC_WARPS * 32, 0, st>>>(ws.R, ws.ev, ws.Vt, (int)W); break;
         default:
             if (M <= 8) eig_kernel<8, false><<<grid, 128, 0, st>>>(ws.R, ws.ev, ws.Vt, M, (int)W);
             else eig_kernel<MAXM, false><<<grid, 128, 0, st>>>(ws.R, ws.ev, ws.Vt, M, (int)W);

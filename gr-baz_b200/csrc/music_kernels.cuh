@@ -567,6 +567,127 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
 }
 
 // ------------------------------------------------------------------------------------------
+// K2 for M = 8..16 (even M): warp-cooperative Jacobi with the matrices in shared memory, one warp
+// per window.  The thread-per-window solver keeps A and V (2 x M x M complex) in local memory
+// for M > 4 and is bound by that traffic (M = 16: ~0.5 M cycles per window per SM); here a sweep is
+// M-1 parallel steps of M/2 disjoint rotations (round-robin ordering): lanes 0..M/2-1 compute the
+// rotations, then all 32 lanes apply them to the columns of A and V and to the rows of A.
+// Output layout and conventions are those of herm_eig_body (ascending, stable, real v[0]).
+// ------------------------------------------------------------------------------------------
+constexpr int EIGC_WARPS = 4;
+
+template <int M>
+__global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double *__restrict__ R, double *__restrict__ evals,
+                                                                   double *__restrict__ Vt, int W)
+{
+    static_assert(M % 2 == 0 && M <= MAXM, "even M only");
+    constexpr int H = M / 2;
+    __shared__ double2 sA[EIGC_WARPS][M * M];
+    __shared__ double2 sV[EIGC_WARPS][M * M];
+    __shared__ double sRot[EIGC_WARPS][H][4];  // c, Re(s w), Im(s w), unused
+    __shared__ int sPair[EIGC_WARPS][H][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * EIGC_WARPS + warp;
+    if (w >= W) return;
+    double2 *A = sA[warp], *V = sV[warp];
+    const double2 *Rw = reinterpret_cast<const double2 *>(R) + (size_t)w * M * M;
+    for (int i = lane; i < M * M; i += 32) {
+        A[i] = Rw[i];
+        V[i] = make_double2((i / M == i % M) ? 1.0 : 0.0, 0.0);
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, fro = 0.0;
+        for (int i = lane; i < M * M; i += 32) {
+            const double2 a = A[i];
+            const double e2 = a.x * a.x + a.y * a.y;
+            fro += e2;
+            if (i / M != i % M) off += e2;
+        }
+        off = warp_sum(off);
+        fro = warp_sum(fro);
+        if (off <= 1e-32 * fro || off == 0.0) break;
+        for (int step = 0; step < M - 1; ++step) {
+            if (lane < H) {  // rotation of pair `lane` (circle method: index M-1 stays, the others rotate)
+                int p, q;
+                if (lane == 0) { p = M - 1; q = step; }
+                else { p = (step + lane) % (M - 1); q = (step - lane + (M - 1)) % (M - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                const double2 g2 = A[p * M + q];
+                const double app = A[p * M + p].x, aqq = A[q * M + q].x;
+                const double gg = fma(g2.x, g2.x, g2.y * g2.y);
+                const bool nz = gg > 0.0;
+                const double rg = nz ? rsqrt(gg) : 0.0;
+                double theta = 0.5 * (aqq - app) * rg;
+                theta = fmin(fmax(theta, -1e150), 1e150);
+                const double q1 = fma(theta, theta, 1.0);
+                const double sq = q1 * rsqrt(q1);
+                double t = 1.0 / (fabs(theta) + sq);
+                t = nz ? copysign(t, theta) : 0.0;
+                if (gg != gg) t = gg;  // NaN input stays NaN
+                const double c = rsqrt(fma(t, t, 1.0));
+                const double sn = t * c;
+                sRot[warp][lane][0] = c;
+                sRot[warp][lane][1] = sn * g2.x * rg;
+                sRot[warp][lane][2] = sn * g2.y * rg;
+                sPair[warp][lane][0] = p;
+                sPair[warp][lane][1] = q;
+            }
+            __syncwarp();
+            // columns: B[k][p] = c A[k][p] - conj(sw) A[k][q],  B[k][q] = sw A[k][p] + c A[k][q]   (A and V)
+            for (int it = lane; it < M * H; it += 32) {
+                const int k = it / H, i = it % H;
+                const int p = sPair[warp][i][0], q = sPair[warp][i][1];
+                const double c = sRot[warp][i][0], swr = sRot[warp][i][1], swi = sRot[warp][i][2];
+                {
+                    const double2 ap = A[k * M + p], aq = A[k * M + q];
+                    A[k * M + p] = make_double2(c * ap.x - (swr * aq.x + swi * aq.y), c * ap.y - (swr * aq.y - swi * aq.x));
+                    A[k * M + q] = make_double2(c * aq.x + (swr * ap.x - swi * ap.y), c * aq.y + (swr * ap.y + swi * ap.x));
+                }
+                {
+                    const double2 vp = V[k * M + p], vq = V[k * M + q];
+                    V[k * M + p] = make_double2(c * vp.x - (swr * vq.x + swi * vq.y), c * vp.y - (swr * vq.y - swi * vq.x));
+                    V[k * M + q] = make_double2(c * vq.x + (swr * vp.x - swi * vp.y), c * vq.y + (swr * vp.y + swi * vp.x));
+                }
+            }
+            __syncwarp();
+            // rows: A'[p][k] = c B[p][k] - sw B[q][k],  A'[q][k] = conj(sw) B[p][k] + c B[q][k]
+            for (int it = lane; it < M * H; it += 32) {
+                const int k = it / H, i = it % H;
+                const int p = sPair[warp][i][0], q = sPair[warp][i][1];
+                const double c = sRot[warp][i][0], swr = sRot[warp][i][1], swi = sRot[warp][i][2];
+                const double2 bp = A[p * M + k], bq = A[q * M + k];
+                A[p * M + k] = make_double2(c * bp.x - (swr * bq.x - swi * bq.y), c * bp.y - (swr * bq.y + swi * bq.x));
+                A[q * M + k] = make_double2(c * bq.x + (swr * bp.x + swi * bp.y), c * bq.y + (swr * bp.y - swi * bp.x));
+            }
+            __syncwarp();
+            if (lane < H) {  // exact zeros / real diagonal where the rotation says so
+                const int p = sPair[warp][lane][0], q = sPair[warp][lane][1];
+                A[p * M + q] = make_double2(0.0, 0.0);
+                A[q * M + p] = make_double2(0.0, 0.0);
+                A[p * M + p].y = 0.0;
+                A[q * M + q].y = 0.0;
+            }
+            __syncwarp();
+        }
+    }
+    // ascending, stable ranks; eigenvector j -> slot rank(j), phase fixed so that component 0 is real
+    double *ew = evals + (size_t)w * M;
+    double2 *vw = reinterpret_cast<double2 *>(Vt) + (size_t)w * M * M;
+    for (int it = lane; it < M * M; it += 32) {
+        const int j = it / M, i = it % M;  // column j, component i
+        const double wj = A[j * M + j].x;
+        int rank = 0;
+        for (int l = 0; l < M; ++l) rank += eig_before(A[l * M + l].x, l, wj, j);
+        double pr, pi;
+        eig_phase(V[0 * M + j].x, V[0 * M + j].y, pr, pi);
+        const double2 v = V[i * M + j];
+        vw[rank * M + i] = make_double2(v.x * pr - v.y * pi, i == 0 ? 0.0 : v.x * pi + v.y * pr);
+        if (i == 0) ew[rank] = wj;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Steering table preparation (once per set_table): c64 [K][M] -> fp64 SoA tiles
 //   soa[tile][comp][TILE],  comp = 2i (Re a_i), 2i+1 (Im a_i), 2M (||a||^2); zero padded.
 // Hoists the per-step c64 -> c128 widening of the reference (:110-112) out of the hot loop.
