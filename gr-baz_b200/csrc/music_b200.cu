@@ -21,6 +21,7 @@
 
 #include "music_kernels.cuh"
 #include "music_fused.cuh"
+#include "music_covn.cuh"
 
 using namespace music;
 
@@ -67,6 +68,7 @@ struct music_b200 {
     bool fused_used = false;
     long long *fused_trace = nullptr;  // MUSIC_B200_TRACE=1: per-CTA clock64 trace of the fused kernel (tools/fused_trace.py)
     bool fused = true;       // MUSIC_B200_FUSED=0 forces the three-kernel path
+    bool covn = true;        // MUSIC_B200_COVN=0: M = 8/16 covariance by the v1 LDG tile kernels
     bool scan_fast = true;   // MUSIC_B200_SCAN=general disables the specialised n == 1 kernel
     int cov_tma_stages = 6;  // 0 = LDG tile kernel (MUSIC_B200_COV=ldg), 4 or 6 = TMA ring depth
     // optional per-stage timing (bench.py's roofline leg): events around K1/K2/K3/top-n per chunk
@@ -130,6 +132,23 @@ int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t s
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(st));
     return MUSIC_B200_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
 }
 
 constexpr int NSLOT = 3;           // workspace ring for the cov -> eig/scan software pipeline
@@ -213,6 +232,34 @@ void launch_cov(music_b200 *h, const Workspace &ws, const float *d_in, uint32_t 
         if (stages == 6) cov4_tma_kernel<6><<<grid, COV_WARPS * 32, smem, st>>>(d_in, ws.R, (int)W, N);
         else cov4_tma_kernel<4><<<grid, COV_WARPS * 32, smem, st>>>(d_in, ws.R, (int)W, N);
         h->launches++;
+    } else if ((M == 8 || M == 16) && h->covn && N >= 4 * (COV_CHUNK / (8 * M)) && encode_tiled_fn()) {
+        // TMA-tiled, window staged once per group of warps (music_covn.cuh)
+        CUtensorMap tm;
+        const cuuint64_t gdim[3] = {(cuuint64_t)(2 * M), (cuuint64_t)N, (cuuint64_t)W};
+        const cuuint64_t gstr[2] = {(cuuint64_t)(8 * M), (cuuint64_t)(8 * M) * (cuuint64_t)N};
+        const cuuint32_t box[3] = {(cuuint32_t)(2 * M), (cuuint32_t)(COV_CHUNK / (8 * M)), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult cr = encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_in), gdim, gstr, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr == CUDA_SUCCESS) {
+            constexpr int groups8 = CN_WARPS / CovNJobs<8>::J, groups16 = CN_WARPS / CovNJobs<16>::J;
+            const int groups = M == 8 ? groups8 : groups16;
+            const int grid = std::min<int>(h->sm_count, (int)((W + groups - 1) / groups));
+            if (h->fused_used) cudaStreamWaitEvent(st, h->fused_done, 0);  // shares work_ctr: serialise launches
+            if (M == 8) covN_tma_kernel<8><<<grid, CN_WARPS * 32, CN_SMEM, st>>>(tm, ws.R, (int)W, N, h->work_ctr);
+            else covN_tma_kernel<16><<<grid, CN_WARPS * 32, CN_SMEM, st>>>(tm, ws.R, (int)W, N, h->work_ctr);
+            cudaEventRecord(h->fused_done, st);
+            h->fused_used = true;
+            h->launches++;
+            return;
+        }
+        // (encode failed: fall through is not possible inside this else-if chain; use the tile kernels)
+        const int T = M / 4;
+        const int wpb = 8;
+        cov_tile_kernel<false><<<(unsigned)(((long long)W * T + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, ws.R, (int)W, N, M);
+        cov_tile_kernel<true><<<(unsigned)(((long long)W * (T * (T - 1) / 2) + wpb - 1) / wpb), wpb * 32, 0, st>>>(d_in, ws.R, (int)W, N, M);
+        h->launches += 2;
     } else if (M % 4 == 0) {
         const int T = M / 4;
         const int wpb = 8;
@@ -505,6 +552,9 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         }
         if (const char *e = getenv("MUSIC_B200_SCAN")) h->scan_fast = strcmp(e, "general") != 0;
         if (const char *e = getenv("MUSIC_B200_FUSED")) h->fused = atoi(e) != 0;
+        if (const char *e = getenv("MUSIC_B200_COVN")) h->covn = atoi(e) != 0;
+        CU(h, cudaFuncSetAttribute(covN_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
+        CU(h, cudaFuncSetAttribute(covN_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
         CU(h, cudaEventCreateWithFlags(&h->fused_done, cudaEventDisableTiming));
         CU(h, cudaMalloc(&h->work_ctr, 2 * sizeof(unsigned)));
         CU(h, cudaMemset(h->work_ctr, 0, 2 * sizeof(unsigned)));

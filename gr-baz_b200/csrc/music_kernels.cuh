@@ -507,7 +507,7 @@ __device__ __forceinline__ void herm_eig_body(const double *Rw, double *ew, doub
                     if (i != j) off += e2;
                 }
         }
-        if (off <= 1e-32 * fro || off == 0.0) break;
+        if (off <= (M > 4 ? 1e-29 : 1e-32) * fro || off == 0.0) break;  // see eig_coop_kernel for the M > 4 threshold
         if (STATIC && MA == 4) {
             // parallel (round-robin) ordering: the two rotations of a step touch disjoint rows/columns
             jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 0, 1); jacobi_rotate_bf<MA>(Ar, Ai, Vr, Vi, 2, 3);
@@ -596,6 +596,7 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
         V[i] = make_double2((i / M == i % M) ? 1.0 : 0.0, 0.0);
     }
     __syncwarp();
+    double prev_off = 1e300;
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0.0, fro = 0.0;
         for (int i = lane; i < M * M; i += 32) {
@@ -606,7 +607,10 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
         }
         off = warp_sum(off);
         fro = warp_sum(fro);
-        if (off <= 1e-32 * fro || off == 0.0) break;
+        // rounding keeps the off-diagonal energy of an M x M iterate near 2 M eps^2 ||A||_F^2 (4e-31 at M = 16), so
+        // the M = 4 threshold (1e-32) is unreachable here: stop at 1e-29, or when a sweep no longer helps
+        if (off <= 1e-29 * fro || off == 0.0 || (sweep > 2 && off <= 1e-24 * fro && off >= 0.25 * prev_off)) break;
+        prev_off = off;
         for (int step = 0; step < M - 1; ++step) {
             if (lane < H) {  // rotation of pair `lane` (circle method: index M-1 stays, the others rotate)
                 int p, q;
@@ -652,8 +656,9 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
             }
             __syncwarp();
             // rows: A'[p][k] = c B[p][k] - sw B[q][k],  A'[q][k] = conj(sw) B[p][k] + c B[q][k]
+            // (k fastest across lanes: a row is contiguous, so the accesses are bank-conflict free)
             for (int it = lane; it < M * H; it += 32) {
-                const int k = it / H, i = it % H;
+                const int i = it / M, k = it % M;
                 const int p = sPair[warp][i][0], q = sPair[warp][i][1];
                 const double c = sRot[warp][i][0], swr = sRot[warp][i][1], swi = sRot[warp][i][2];
                 const double2 bp = A[p * M + k], bq = A[q * M + k];
