@@ -4,7 +4,9 @@
 // window from global memory, i.e. a window is read 2x (M = 8) to 4x (M = 16) through L2 and the loads
 // are not overlapped with the arithmetic.  Here a group of J warps (J = 2 for M = 8, J = 8 for M = 16)
 // shares one ring of 4 KiB stages filled by cp.async.bulk.tensor (SASS UTMALDG) through a 3-D tensor
-// map {2M floats, N snapshots, W windows} with CU_TENSOR_MAP_SWIZZLE_128B: the hardware XOR-swizzle
+// map {32 floats = one 128-byte row (1 snapshot at M = 16, 2 at M = 8), N*M/16 rows, W windows}, box
+// {32, 32, 1}, with CU_TENSOR_MAP_SWIZZLE_128B (rows narrower than the 128-byte swizzle span are padded
+// to it in shared memory, hence the 128-byte row view): the hardware XOR-swizzle
 // of the 16-byte units makes "lane <-> snapshot row, same unit" reads bank-conflict free (a plain 1-D
 // copy would put all lanes on the same banks for 64/128-byte rows), and out-of-range rows of the last
 // chunk of a window are zero-filled by TMA (zeros add nothing to x x^H).
@@ -101,6 +103,9 @@ template <int M>
 __global__ void __launch_bounds__(CN_WARPS * 32, 1)
 covN_tma_kernel(const __grid_constant__ CUtensorMap tm, double *__restrict__ R, int W, int N, unsigned *__restrict__ work_ctr)
 {
+    // address of the tensor map in param space, taken in the kernel body (not inside a lambda: a by-reference
+    // capture would make the compiler copy the map to local memory, which TMA cannot read)
+    const unsigned long long tm_addr = reinterpret_cast<unsigned long long>(&tm);
     constexpr int J = CovNJobs<M>::J;
     constexpr int G = CN_WARPS / J;                 // window groups per CTA
     constexpr int SG = CN_STAGES_TOTAL / G;         // stages per group
@@ -142,7 +147,7 @@ covN_tma_kernel(const __grid_constant__ CUtensorMap tm, double *__restrict__ R, 
         const int slot = (int)(issued % SG);
         mbar_expect_tx(full0 + 8 * slot, COV_CHUNK);
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                     ::"r"(ring0 + slot * COV_CHUNK), "l"(&tm), "r"(0), "r"(iq * ROWS), "r"(iw), "r"(full0 + 8 * slot)
+                     ::"r"(ring0 + slot * COV_CHUNK), "l"(tm_addr), "r"(0), "r"(iq * 32), "r"(iw), "r"(full0 + 8 * slot)
                      : "memory");
         ++issued;
         if (++iq == cpw) { iq = 0; claim(); }
