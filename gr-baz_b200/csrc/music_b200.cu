@@ -232,14 +232,14 @@ void launch_cov(music_b200 *h, const Workspace &ws, const float *d_in, uint32_t 
         if (stages == 6) cov4_tma_kernel<6><<<grid, COV_WARPS * 32, smem, st>>>(d_in, ws.R, (int)W, N);
         else cov4_tma_kernel<4><<<grid, COV_WARPS * 32, smem, st>>>(d_in, ws.R, (int)W, N);
         h->launches++;
-    } else if ((M == 8 || M == 16) && h->covn && N >= 4 * (COV_CHUNK / (8 * M)) && N % (16 / M) == 0 && encode_tiled_fn()) {
+    } else if ((M == 8 || M == 16) && h->covn && N >= 128 && N % (16 / M) == 0 && encode_tiled_fn()) {
         // TMA-tiled, window staged once per group of warps (music_covn.cuh)
         CUtensorMap tm;
         // rows of 128 bytes (SPR snapshots each): with SWIZZLE_128B a narrower inner box would be padded to the span
         const int SPR = 16 / M;  // snapshots per 128-byte row
         const cuuint64_t gdim[3] = {32u, (cuuint64_t)(N / SPR), (cuuint64_t)W};
         const cuuint64_t gstr[2] = {128u, (cuuint64_t)(8 * M) * (cuuint64_t)N};
-        const cuuint32_t box[3] = {32u, 32u, 1u};
+        const cuuint32_t box[3] = {32u, (cuuint32_t)(M == 8 ? 32 * CovNJobs<8>::STEPS * 8 * 8 / 128 : 32 * CovNJobs<16>::STEPS * 8 * 16 / 128), 1u};  // one stage
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         const CUresult cr = encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_in), gdim, gstr, box, estr,
                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
