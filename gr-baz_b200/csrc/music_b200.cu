@@ -22,6 +22,7 @@
 #include "music_kernels.cuh"
 #include "music_fused.cuh"
 #include "music_covn.cuh"
+#include "music_steer.cuh"
 
 using namespace music;
 
@@ -56,6 +57,11 @@ struct music_b200 {
 
     DeviceTable table[2];
     int cur_table = 0;
+    double *steer_pos = nullptr;   // device copy of the element positions (set_geometry)
+    unsigned *steer_count = nullptr;
+    int *steer_list = nullptr;
+    float *steer_vals = nullptr;
+    unsigned steer_guarded = 0;    // entries of the last built table re-evaluated with the host libm
 
     // fp64 workspace slots (R, eigenvalues, sorted eigenvectors, optional strengths) and the two
     // internal streams of the cov -> eig/scan pipeline
@@ -116,10 +122,10 @@ int fail(music_b200 *h, int code, const char *fmt, ...)
 uint32_t table_tiles(uint32_t K) { return (uint32_t)((K + TILE - 1) / TILE); }
 size_t soa_doubles(uint32_t K, uint32_t M) { return (size_t)table_tiles(K) * (2 * M + 1) * TILE; }
 
-int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t st)
+// derived layouts (fp64 SoA tiles, TF32 hi/lo MMA fragments) of the c64 table already in t.c64
+int finish_table(music_b200 *h, int slot, cudaStream_t st)
 {
     DeviceTable &t = h->table[slot];
-    CU(h, cudaMemcpyAsync(t.c64, table_c64, (size_t)h->K * h->m * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
     const int ntiles = (int)table_tiles(h->K);
     prep_table_kernel<<<ntiles, TILE, 0, st>>>(reinterpret_cast<const float2 *>(t.c64), t.soa, (int)h->K, (int)h->m);
     h->launches++;
@@ -132,6 +138,60 @@ int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t s
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(st));
     return MUSIC_B200_OK;
+}
+
+int upload_table(music_b200 *h, int slot, const float *table_c64, cudaStream_t st)
+{
+    CU(h, cudaMemcpyAsync(h->table[slot].c64, table_c64, (size_t)h->K * h->m * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    return finish_table(h, slot, st);
+}
+
+// Steering table built on the device from the element positions (music_steer.cuh), then patched at the
+// few entries whose float32 rounding could depend on the libm in use.
+int build_table(music_b200 *h, int slot, const double *pos_xy, double lambda, cudaStream_t st)
+{
+    DeviceTable &t = h->table[slot];
+    const int K = (int)h->K, M = (int)h->m;
+    if (!h->steer_pos) {
+        CU(h, cudaMalloc(&h->steer_pos, sizeof(double) * 2 * MUSIC_B200_MAX_M));
+        CU(h, cudaMalloc(&h->steer_count, sizeof(unsigned)));
+        CU(h, cudaMalloc(&h->steer_list, sizeof(int) * STEER_GUARD_CAP));
+        CU(h, cudaMalloc(&h->steer_vals, sizeof(float) * 2 * STEER_GUARD_CAP));
+    }
+    CU(h, cudaMemcpyAsync(h->steer_pos, pos_xy, sizeof(double) * 2 * M, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemsetAsync(h->steer_count, 0, sizeof(unsigned), st));
+    steer_table_kernel<<<(K * M + 255) / 256, 256, 0, st>>>(h->steer_pos, lambda, K, M, reinterpret_cast<float2 *>(t.c64),
+                                                           h->steer_count, h->steer_list);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    unsigned cnt = 0;
+    CU(h, cudaMemcpyAsync(&cnt, h->steer_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    h->steer_guarded = cnt;
+    static const bool no_guard = getenv("MUSIC_B200_STEER_NOGUARD") != nullptr;  // diagnostics: raw device table
+    if (no_guard) return finish_table(h, slot, st);
+    if (cnt > (unsigned)STEER_GUARD_CAP) {
+        // more boundary cases than the list holds (a degenerate geometry, e.g. all elements at the origin, makes
+        // every entry exactly (1, 0)): evaluate every entry the literal way
+        std::vector<float> full((size_t)K * M * 2);
+        for (int k = 0; k < K; ++k)
+            for (int a = 0; a < M; ++a) steer_entry_host(pos_xy, lambda, K, k, a, &full[2 * ((size_t)k * M + a)], &full[2 * ((size_t)k * M + a) + 1]);
+        CU(h, cudaMemcpyAsync(t.c64, full.data(), full.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(h, cudaStreamSynchronize(st));
+    } else if (cnt) {
+        std::vector<int> list(cnt);
+        CU(h, cudaMemcpyAsync(list.data(), h->steer_list, sizeof(int) * cnt, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        std::vector<float> vals(2 * (size_t)cnt);
+        for (unsigned i = 0; i < cnt; ++i) steer_entry_host(pos_xy, lambda, K, list[i] / M, list[i] % M, &vals[2 * i], &vals[2 * i + 1]);
+        CU(h, cudaMemcpyAsync(h->steer_vals, vals.data(), vals.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        steer_patch_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(reinterpret_cast<float2 *>(t.c64), h->steer_list,
+                                                            reinterpret_cast<const float2 *>(h->steer_vals), (int)cnt);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        CU(h, cudaStreamSynchronize(st));  // vals is a local
+    }
+    return finish_table(h, slot, st);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -597,6 +657,40 @@ int music_b200_set_table(music_b200 *h, const float *table_c64)
     return MUSIC_B200_OK;
 }
 
+int music_b200_set_geometry(music_b200 *h, const double *positions_xy, double wavelength, uint32_t *guarded)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (!positions_xy) return fail(h, MUSIC_B200_EINVAL, "element positions must not be NULL");
+    if (!(wavelength > 0.0) || !std::isfinite(wavelength)) return fail(h, MUSIC_B200_EINVAL, "wavelength must be positive and finite");
+    for (uint32_t i = 0; i < 2 * h->m; ++i)
+        if (!std::isfinite(positions_xy[i])) return fail(h, MUSIC_B200_EINVAL, "element positions must be finite");
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());  // as in set_table(): the slot being rebuilt must be idle
+    const int slot = h->cur_table ^ 1;
+    int rc = build_table(h, slot, positions_xy, wavelength, h->streams[0]);
+    if (rc) return rc;
+    h->cur_table = slot;
+    if (guarded) *guarded = h->steer_guarded;
+    return MUSIC_B200_OK;
+}
+
+void music_b200_steer_entry_host(const double *positions_xy, double wavelength, uint32_t resolution, uint32_t step,
+                                 uint32_t antenna, float *re_im)
+{
+    steer_entry_host(positions_xy, wavelength, (int)resolution, (int)step, (int)antenna, &re_im[0], &re_im[1]);
+}
+
+int music_b200_get_table(music_b200 *h, float *table_c64)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (!table_c64) return fail(h, MUSIC_B200_EINVAL, "output table must not be NULL");
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpy(table_c64, h->table[h->cur_table].c64, (size_t)h->K * h->m * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    return MUSIC_B200_OK;
+}
+
 int music_b200_process_device_ex(music_b200 *h, const float *d_in_c64, uint32_t nwindows, float *d_angles,
                                  float *d_levels, float *d_spectrum, int32_t *d_bins, double *d_P64, double *d_R,
                                  double *d_eigvals, void *stream)
@@ -673,6 +767,7 @@ void music_b200_destroy(music_b200 *h)
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->fused_trace);
     cudaFree(h->work_ctr);
+    cudaFree(h->steer_pos); cudaFree(h->steer_count); cudaFree(h->steer_list); cudaFree(h->steer_vals);
     if (h->fused_done) cudaEventDestroy(h->fused_done);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->table[i].c64); cudaFree(h->table[i].soa); cudaFree(h->table[i].fz); cudaFree(h->table[i].na_max);

@@ -77,6 +77,27 @@ class music_doa(object):
         sys.stderr.write("[%s<%i>] Updating array response\n" % (self.name(), self._unique_id))  # :65
         _capi.check(self._lib.music_b200_set_table(self._h, table.ctypes.data), self._h)
 
+    # -- extension: retune on the device ---------------------
+    def set_array_geometry(self, antenna_array, l):
+        """Device-side equivalent of ``set_array_response(calculate_antenna_array_response(
+        antenna_array, resolution, l))`` (/root/reference/python/music_doa_helper.py:32-46,
+        :100-103): ``antenna_array`` = element positions [[x, y], ...] in metres (already scaled by
+        the spacing, :56), ``l`` = wavelength.  Returns the number of entries the library
+        re-evaluated with the host libm to keep the table bit-identical to the Python helper's."""
+        pos = np.ascontiguousarray(np.asarray(antenna_array, dtype=np.float64))
+        if pos.shape != (self.m, 2):
+            raise ValueError("antenna_array must hold m = %d [x, y] positions" % self.m)
+        guarded = ctypes.c_uint32(0)
+        _capi.check(self._lib.music_b200_set_geometry(self._h, pos.ctypes.data, float(l), ctypes.byref(guarded)), self._h)
+        return int(guarded.value)
+
+    def array_response_c64(self):
+        """The table in use, as complex64 (resolution, m) - what the block holds after the SWIG
+        conversion (swig/baz_swig.i:564)."""
+        out = np.empty((self.resolution, self.m), np.complex64)
+        _capi.check(self._lib.music_b200_get_table(self._h, out.ctypes.data), self._h)
+        return out
+
     def work(self, noutput_items, input_items, output_items):
         """input_items[0]: complex64 (noutput_items, nsamples); output_items: 1..3 float32 arrays
         (angles (., n), levels (., n), spectrum (., resolution)).  Returns items produced."""

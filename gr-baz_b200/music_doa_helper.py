@@ -36,7 +36,7 @@ def calculate_antenna_array_response(antenna_array, angular_resolution, l):
 
 class music_doa_helper(object):
     def __init__(self, m, n, nsamples, angular_resolution, frequency, array_spacing, antenna_array,
-                 output_spectrum=False, device=0):
+                 output_spectrum=False, device=0, device_table=False):
         self.m = m
         self.n = n
         self.nsamples = nsamples
@@ -44,6 +44,9 @@ class music_doa_helper(object):
         self.l = 299792458.0 / frequency  # :55
         self.antenna_array = [[array_spacing * x, array_spacing * y] for [x, y] in antenna_array]  # :56
         self.output_spectrum = bool(output_spectrum)
+        # extension: device_table=True makes set_frequency() rebuild the table on the GPU
+        # (music_b200_set_geometry) instead of the K x M Python loop + re-marshalling; same table, bit for bit
+        self.device_table = bool(device_table)
 
         if (nsamples % m) != 0:
             raise Exception("nsamples must be multiple of m")  # :58-59
@@ -62,6 +65,10 @@ class music_doa_helper(object):
     def set_frequency(self, frequency):
         """:100-103"""
         self.l = 299792458.0 / frequency
+        if self.device_table:
+            self.impl.set_array_geometry(self.antenna_array, self.l)
+            self.array_response = None  # lives on the device; impl.array_response_c64() reads it back
+            return
         self.array_response = calculate_antenna_array_response(self.antenna_array, self.angular_resolution, self.l)
         self.impl.set_array_response(self.array_response)
 

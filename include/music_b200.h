@@ -63,6 +63,30 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
 int music_b200_set_table(music_b200 *h, const float *table_c64);
 
 /*
+ * Retune without marshalling a table: builds the array response ON THE DEVICE from the element
+ * positions and the wavelength, i.e. replaces calculate_antenna_array_response() + the SWIG
+ * complex128 -> complex64 conversion + set_array_response()
+ * (/root/reference/python/music_doa_helper.py:29-46, :100-103; swig/baz_swig.i:564) by one call.
+ * positions_xy: [m][2] doubles in metres, already multiplied by array_spacing
+ * (music_doa_helper.py:56); wavelength = 299792458 / frequency (:55, :101).
+ * The resulting table is bit-identical to the one the Python helper computes on this host:
+ * entries whose float32 rounding could depend on the last bits of sin/cos are re-evaluated
+ * with the host libm; *guarded (may be NULL) receives how many (typically ~3e-5 of 2*m*K).
+ * Same locking and double buffering as music_b200_set_table().
+ */
+int music_b200_set_geometry(music_b200 *h, const double *positions_xy, double wavelength, uint32_t *guarded);
+
+/*
+ * Test hook (no device needed): the host-libm evaluation of one table entry that
+ * music_b200_set_geometry() uses for the guarded entries; re_im = {Re, Im} as float32.
+ */
+void music_b200_steer_entry_host(const double *positions_xy, double wavelength, uint32_t resolution, uint32_t step,
+                                 uint32_t antenna, float *re_im);
+
+/* Copies the table currently in use (float[resolution][m][2]) back to host memory. */
+int music_b200_get_table(music_b200 *h, float *table_c64);
+
+/*
  * Replaces the body of baz_music_doa::work() (/root/reference/lib/baz_music_doa.cc:72-161)
  * for `nwindows` consecutive input items held in HOST memory (what the GNU Radio scheduler
  * hands to work(): input_items[0], output_items[0..2]).  Host<->device copies are done

@@ -90,6 +90,26 @@ void baz_music_doa::set_array_response(const array_response_t &array_response)
     if (rc != MUSIC_B200_OK) throw std::runtime_error(std::string("music_doa: ") + music_b200_last_error(d_handle));
 }
 
+/* Extension (not in the reference): retune from the element positions; the table is built on the device
+   (music_b200_set_geometry) and is bit-identical to calculate_antenna_array_response() + set_array_response()
+   of /root/reference/python/music_doa_helper.py:32-46, :100-103. */
+void baz_music_doa::set_array_geometry(const std::vector<std::vector<double> > &positions_xy, double wavelength)
+{
+    if (positions_xy.size() != d_m) throw std::invalid_argument("music_doa: positions_xy.size() != m");
+    std::vector<double> flat;
+    flat.reserve(2 * (size_t)d_m);
+    for (size_t i = 0; i < positions_xy.size(); ++i) {
+        if (positions_xy[i].size() != 2) throw std::invalid_argument("music_doa: each position must be [x, y]");
+        flat.push_back(positions_xy[i][0]);
+        flat.push_back(positions_xy[i][1]);
+    }
+    fprintf(stderr, "[%s<%li>] Updating array response\n", name().c_str(), unique_id());
+    gr::thread::scoped_lock guard(d_mutex);
+    const int rc = music_b200_set_geometry(d_handle, flat.data(), wavelength, NULL);
+    if (rc == MUSIC_B200_EINVAL) throw std::invalid_argument(std::string("music_doa: ") + music_b200_last_error(d_handle));
+    if (rc != MUSIC_B200_OK) throw std::runtime_error(std::string("music_doa: ") + music_b200_last_error(d_handle));
+}
+
 int baz_music_doa::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items)
 {
     if (noutput_items <= 0) return 0;

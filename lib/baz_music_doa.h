@@ -49,6 +49,8 @@ public:
     int work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items);
 
     void set_array_response(const array_response_t &array_response);
+    /* extension: device-side table build from element positions [m][x, y] (metres) and the wavelength */
+    void set_array_geometry(const std::vector<std::vector<double> > &positions_xy, double wavelength);
 
     /* Integer peak-bin indices of the items produced by the last work() call, [items][n]
      * (not in the reference; -1 marks a slot the reference would leave at (0, 0)). */

@@ -30,6 +30,7 @@ private:
 	baz_music_doa(unsigned int m, unsigned int n, unsigned int nsamples, const array_response_t& array_response, unsigned int resolution);
 public:
 	void set_array_response(const std::vector<std::vector<gr_complex> >& array_response);
+	void set_array_geometry(const std::vector<std::vector<double> >& positions_xy, double wavelength);
 };
 
 #endif // MUSIC_B200_FOUND
