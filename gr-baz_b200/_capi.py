@@ -43,6 +43,10 @@ def load():
         L.music_b200_create.restype = ctypes.c_int
         L.music_b200_set_table.argtypes = [vp, fp]
         L.music_b200_set_table.restype = ctypes.c_int
+        L.music_b200_process_planar_host.argtypes = [vp, fp, u32, u32, fp, fp, fp, fp]
+        L.music_b200_process_planar_host.restype = ctypes.c_int
+        L.music_b200_process_planar_device.argtypes = [vp, fp, u32, u32, fp, fp, fp, fp, vp]
+        L.music_b200_process_planar_device.restype = ctypes.c_int
         L.music_b200_set_geometry.argtypes = [vp, fp, ctypes.c_double, ctypes.POINTER(u32)]
         L.music_b200_set_geometry.restype = ctypes.c_int
         L.music_b200_steer_entry_host.argtypes = [fp, ctypes.c_double, u32, u32, u32, fp]
@@ -74,7 +78,8 @@ def load():
 EXPORTS = [
     "music_b200_version", "music_b200_create", "music_b200_set_table", "music_b200_set_geometry",
     "music_b200_get_table", "music_b200_steer_entry_host", "music_b200_process_host",
-    "music_b200_process_device", "music_b200_process_device_ex", "music_b200_launch_count",
+    "music_b200_process_device", "music_b200_process_device_ex", "music_b200_process_planar_host",
+    "music_b200_process_planar_device", "music_b200_launch_count",
     "music_b200_set_stage_timing", "music_b200_get_stage_times", "music_b200_debug_fused_trace",
     "music_b200_last_error", "music_b200_destroy",
 ]

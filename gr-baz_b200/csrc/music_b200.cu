@@ -23,6 +23,7 @@
 #include "music_fused.cuh"
 #include "music_covn.cuh"
 #include "music_steer.cuh"
+#include "music_planar.cuh"
 
 using namespace music;
 
@@ -403,14 +404,28 @@ int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, float *d_ang
 // with K2+K3 (FP64-only) of sub-batch j, each sub-batch owning one workspace slot.  `st` is
 // ordered before the first and after the last piece of work.  Small calls, and calls made while
 // stage timing is on, run serially on `st`.
+// K1 on planar streams (music_planar.cuh): windows first .. first + W - 1 of the call
+void launch_cov_planar(music_b200 *h, const Workspace &ws, const PlanarStreams &S, unsigned long long first_snapshot,
+                       unsigned hop, uint32_t W, cudaStream_t st)
+{
+    const int M = (int)h->m, N = (int)h->N, T = (M + 3) / 4, wpb = 8;
+    cov_planar_kernel<false><<<(unsigned)(((long long)W * T + wpb - 1) / wpb), wpb * 32, 0, st>>>(S, first_snapshot, hop, ws.R, (int)W, N, M);
+    h->launches++;
+    if (T > 1) {
+        const long long items = (long long)W * (T * (T - 1) / 2);
+        cov_planar_kernel<true><<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, 0, st>>>(S, first_snapshot, hop, ws.R, (int)W, N, M);
+        h->launches++;
+    }
+}
+
 int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d_ang, float *d_lvl, float *d_spec,
                    int32_t *d_bins, double *d_P64, double *d_R, double *d_ev, cudaStream_t st, int first_slot,
-                   bool allow_pipeline)
+                   bool allow_pipeline, const PlanarStreams *planar = nullptr, unsigned hop = 0)
 {
     if (nwindows == 0) return MUSIC_B200_OK;
-    if (!d_in || !d_ang) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 and d_angles must not be NULL");
-    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 must be 16-byte aligned");
-    if (h->fused && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
+    if ((!planar && !d_in) || !d_ang) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 and d_angles must not be NULL");
+    if (!planar && (reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 must be 16-byte aligned");
+    if (!planar && h->fused && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
         // whole call in one persistent launch (music_fused.cuh); no workspace involved
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
@@ -452,7 +467,8 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         if (ws.used) CU(h, cudaStreamWaitEvent(s_cov, ws.scan_done, 0));  // slot free again
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], s_cov);
-        launch_cov(h, ws, d_in + (size_t)w0 * h->nsamples * 2, W, s_cov);
+        if (planar) launch_cov_planar(h, ws, *planar, (unsigned long long)w0 * hop, hop, W, s_cov);
+        else launch_cov(h, ws, d_in + (size_t)w0 * h->nsamples * 2, W, s_cov);
         if (tev) cudaEventRecord(tev[1], s_cov);
         if (pipe) {
             CU(h, cudaEventRecord(ws.cov_done, s_cov));
@@ -654,6 +670,78 @@ int music_b200_set_table(music_b200 *h, const float *table_c64)
     int rc = upload_table(h, slot, table_c64, h->streams[0]);
     if (rc) return rc;
     h->cur_table = slot;
+    return MUSIC_B200_OK;
+}
+
+int music_b200_process_planar_device(music_b200 *h, const float *const *d_streams, uint32_t hop, uint32_t nwindows,
+                                     float *d_angles, float *d_levels, float *d_spectrum, int32_t *d_bins, void *stream)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (nwindows == 0) return MUSIC_B200_OK;
+    if (!d_streams) return fail(h, MUSIC_B200_EINVAL, "d_streams must not be NULL");
+    if (hop == 0) return fail(h, MUSIC_B200_EINVAL, "hop must be >= 1 snapshot");
+    PlanarStreams S;
+    for (uint32_t r = 0; r < MAXM; ++r) S.p[r] = nullptr;
+    for (uint32_t r = 0; r < h->m; ++r) {
+        if (!d_streams[r] || (reinterpret_cast<uintptr_t>(d_streams[r]) & 7u) != 0)
+            return fail(h, MUSIC_B200_EINVAL, "antenna stream %u must be a non-NULL, 8-byte aligned device pointer", r);
+        S.p[r] = reinterpret_cast<const float2 *>(d_streams[r]);
+    }
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    return enqueue_device(h, nullptr, nwindows, d_angles, d_levels, d_spectrum, d_bins, nullptr, nullptr, nullptr,
+                          static_cast<cudaStream_t>(stream), 0, false, &S, hop);
+}
+
+int music_b200_process_planar_host(music_b200 *h, const float *const *streams, uint32_t hop, uint32_t nwindows,
+                                   float *angles, float *levels, float *spectrum, int32_t *bins)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (nwindows == 0) return MUSIC_B200_OK;
+    if (!streams || !angles) return fail(h, MUSIC_B200_EINVAL, "streams and angles must not be NULL");
+    if (hop == 0) return fail(h, MUSIC_B200_EINVAL, "hop must be >= 1 snapshot");
+    for (uint32_t r = 0; r < h->m; ++r)
+        if (!streams[r]) return fail(h, MUSIC_B200_EINVAL, "antenna stream %u must not be NULL", r);
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    // staging holds cap * m * N samples; a chunk of C windows needs m * ((C - 1) * hop + N) of them, laid out planar
+    const size_t N = h->N;
+    size_t cap = std::max<size_t>(SCAN_B, ((size_t)32 << 20) / ((size_t)h->nsamples * 8));
+    cap = std::max<size_t>(cap, ((size_t)hop + N - 1) / N + 1);  // at least one window when hop > N
+    int rc = ensure_host_staging(h, (uint32_t)cap, spectrum != nullptr);
+    if (rc) return rc;
+    cap = h->host_chunk;
+    uint32_t chunk = (uint32_t)std::min<size_t>(cap, 1 + (cap * N - N) / hop);
+    chunk = std::min(chunk, (nwindows + 1) / 2 > SCAN_B ? (nwindows + 1) / 2 : nwindows);
+    chunk = std::max<uint32_t>(1, chunk);
+    int it = 0;
+    rc = MUSIC_B200_OK;
+    for (uint32_t w0 = 0; w0 < nwindows && rc == MUSIC_B200_OK; w0 += chunk, ++it) {
+        const int s = it & 1;
+        const uint32_t W = std::min(chunk, nwindows - w0);
+        cudaStream_t st = h->streams[s];
+        if (it >= 2) CU(h, cudaStreamSynchronize(st));
+        const size_t seg = (size_t)(W - 1) * hop + N;  // snapshots of each stream this chunk touches
+        PlanarStreams S;
+        for (uint32_t r = 0; r < MAXM; ++r) S.p[r] = nullptr;
+        for (uint32_t r = 0; r < h->m; ++r) {
+            float *dst = h->d_in[s] + (size_t)r * seg * 2;
+            CU(h, cudaMemcpyAsync(dst, streams[r] + ((size_t)w0 * hop) * 2, seg * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+            S.p[r] = reinterpret_cast<const float2 *>(dst);
+        }
+        rc = enqueue_device(h, nullptr, W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
+                            nullptr, nullptr, nullptr, st, s, false, &S, hop);
+        if (rc) break;
+        CU(h, cudaMemcpyAsync(angles + (size_t)w0 * h->n, h->d_ang[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (levels) CU(h, cudaMemcpyAsync(levels + (size_t)w0 * h->n, h->d_lvl[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (bins) CU(h, cudaMemcpyAsync(bins + (size_t)w0 * h->n, h->d_bins[s], (size_t)W * h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (spectrum) CU(h, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
+    cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    if (rc) return rc;
+    if (e0 != cudaSuccess || e1 != cudaSuccess)
+        return fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
     return MUSIC_B200_OK;
 }
 

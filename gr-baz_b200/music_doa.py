@@ -136,6 +136,49 @@ class music_doa(object):
             self._h, d_in, int(nwindows), d_angles, d_levels, d_spectrum, d_bins, d_P64, d_R, d_eigvals, stream)
         _capi.check(rc, self._h)
 
+    # -- extension: planar antenna streams, windows by pointer arithmetic
+    def work_planar(self, noutput_items, input_items, output_items, hop=None):
+        """``input_items``: m C-contiguous complex64 1-D arrays, one per antenna, each holding at least
+        ``(noutput_items - 1) * hop + N`` samples (N = nsamples / m); window w is
+        ``x_w(r, c) = input_items[r][w * hop + c]``.  ``hop`` defaults to N (back-to-back vectors, what
+        interleave + stream_to_vector feed the reference block); ``hop < N`` slides the window like
+        /root/reference/lib/baz_overlap.cc:107-129 without copying the overlap.  Outputs as in work()."""
+        W = int(noutput_items)
+        if W <= 0:
+            return 0
+        N = self.nsamples // self.m
+        hop = N if hop is None else int(hop)
+        if hop < 1:
+            raise ValueError("hop must be >= 1")
+        if len(input_items) != self.m:
+            raise ValueError("one input stream per antenna (m = %d)" % self.m)
+        need = (W - 1) * hop + N
+        for x in input_items:
+            if x.dtype != np.complex64 or x.ndim != 1 or not x.flags["C_CONTIGUOUS"] or x.size < need:
+                raise ValueError("each antenna stream must be a C-contiguous 1-D complex64 array of >= %d samples" % need)
+        outs = list(output_items)
+        if not 1 <= len(outs) <= 3:
+            raise ValueError("1 to 3 output ports")
+        sizes = [self.n, self.n, self.resolution]
+        for o, sz in zip(outs, sizes):
+            if o.dtype != np.float32 or not o.flags["C_CONTIGUOUS"] or o.size < W * sz:
+                raise ValueError("output buffers must be C-contiguous float32 of the port's item size")
+        ptrs = (ctypes.c_void_p * self.m)(*[x.ctypes.data for x in input_items])
+        self._last_bins = np.empty((W, self.n), np.int32)
+        rc = self._lib.music_b200_process_planar_host(
+            self._h, ptrs, hop, W, outs[0].ctypes.data, outs[1].ctypes.data if len(outs) > 1 else None,
+            outs[2].ctypes.data if len(outs) > 2 else None, self._last_bins.ctypes.data)
+        _capi.check(rc, self._h)
+        return W
+
+    def process_planar_device(self, d_streams, hop, nwindows, d_angles, d_levels=None, d_spectrum=None, d_bins=None, stream=None):
+        """Raw device-pointer entry: ``d_streams`` = m device addresses (ints) of the antenna streams."""
+        if len(d_streams) != self.m:
+            raise ValueError("one device stream per antenna (m = %d)" % self.m)
+        ptrs = (ctypes.c_void_p * self.m)(*[int(p) for p in d_streams])
+        rc = self._lib.music_b200_process_planar_device(self._h, ptrs, int(hop), int(nwindows), d_angles, d_levels, d_spectrum, d_bins, stream)
+        _capi.check(rc, self._h)
+
     def set_stage_timing(self, enable):
         _capi.check(self._lib.music_b200_set_stage_timing(self._h, 1 if enable else 0), self._h)
 

@@ -63,6 +63,24 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
 int music_b200_set_table(music_b200 *h, const float *table_c64);
 
 /*
+ * Planar input: one c64 stream per antenna instead of interleaved items.  Window w is
+ *     x_w(r, c) = streams[r][w * hop + c],   r < m, c < N = nsamples / m,
+ * i.e. what the flowgraph in front of the reference block builds on the CPU by interleaving the
+ * antenna streams (/root/reference/lib/baz_interleaver.cc:152-229), cutting vectors and, for
+ * sliding windows, re-copying the overlap (/root/reference/lib/baz_overlap.cc:107-129) before
+ * baz_music_doa::work() reshapes it back (/root/reference/lib/baz_music_doa.cc:82-84).
+ * hop == N: back-to-back windows; hop < N: windows overlap by N - hop snapshots; hop > N: gaps.
+ * Each stream must hold (nwindows - 1) * hop + N samples.  Outputs as in process_host/_device.
+ * Results are identical to process_*() on the interleaved windows.
+ *   _host  : streams[r] are host pointers (copied to the device in chunks, planar, no interleave)
+ *   _device: d_streams is a HOST array of m device pointers (8-byte aligned), work is enqueued on `stream`
+ */
+int music_b200_process_planar_host(music_b200 *h, const float *const *streams, uint32_t hop, uint32_t nwindows,
+                                   float *angles, float *levels, float *spectrum, int32_t *bins);
+int music_b200_process_planar_device(music_b200 *h, const float *const *d_streams, uint32_t hop, uint32_t nwindows,
+                                     float *d_angles, float *d_levels, float *d_spectrum, int32_t *d_bins, void *stream);
+
+/*
  * Retune without marshalling a table: builds the array response ON THE DEVICE from the element
  * positions and the wavelength, i.e. replaces calculate_antenna_array_response() + the SWIG
  * complex128 -> complex64 conversion + set_array_response()
