@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--windows", type=int, default=0, help="windows per step per GPU (default: config's, capped by memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the planar-input and device-retune legs (SURVEY 8(f) rows)")
     return ap.parse_args()
 
 
@@ -408,6 +409,58 @@ def run_ours(args):
                "api": "music_doa.work() -> music_b200_process_host (pinned host buffers)"}
         assert np.array_equal(blk.last_bins(), bins_h[:We]), "host path and device path disagree"
 
+    # ---- SURVEY 8(f) rows built so far, same workload (untimed w.r.t. the headline; rank 0, N = 1) ----------
+    next_rows = None
+    if rank == 0 and G == 1 and not args.no_next_rows:
+        next_rows = {}
+        N, M = cfg["snapshots"], cfg["m"]
+        # (f2) planar antenna streams: the same samples as d_in, de-interleaved once (setup, untimed)
+        Wp = min(W, 4096)
+        planar = d_in[:Wp].view(Wp, N, M, 2).permute(2, 0, 1, 3).contiguous().view(M, Wp * N * 2)
+        ptrs = [planar[r].data_ptr() for r in range(M)]
+        d_bp = torch.empty((2 * Wp, n), dtype=torch.int32, device=dev)
+        d_ap = torch.empty((2 * Wp, n), dtype=torch.float32, device=dev)
+        for name, hop, Wn in (("planar_hop_N", N, Wp), ("planar_hop_N_over_2", N // 2, 2 * Wp - 1)):
+            for _ in range(2):
+                blk.process_planar_device(ptrs, hop, Wn, d_ap.data_ptr(), None, None, d_bp.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(3, min(args.steps, 10))
+            p0.record(stream)
+            for _ in range(reps):
+                blk.process_planar_device(ptrs, hop, Wn, d_ap.data_ptr(), None, None, d_bp.data_ptr(), stream.cuda_stream)
+            p1.record(stream)
+            torch.cuda.synchronize()
+            pms = p0.elapsed_time(p1) / reps
+            row = {"value": Wn / (pms * 1e-3), "unit": "windows/s", "ms_per_step": pms, "windows_per_step": Wn, "hop": hop,
+                   "hbm_bytes_per_window": 8 * M * hop + 12 * n,
+                   "api": "music_b200_process_planar_device (M device streams, no interleaved copy)"}
+            if hop == N:
+                row["bins_equal_interleaved_path"] = bool(torch.equal(d_bp[:Wp], d_bins2[(stepno[0] - 1) & 1 if G > 1 else 0][:Wp]))
+            next_rows[name] = row
+        del planar
+        # (f1) retune: device table build vs the reference's Python loop + re-marshalling
+        from gr_baz_b200.music_doa_helper import calculate_antenna_array_response
+        pos = [[synth.SPACING * x, synth.SPACING * y] for x, y in cfg["antenna_array"]]
+        lam = synth.C_LIGHT / (synth.FREQUENCY * 1.01)
+        blkx = music_doa(M, n, cfg["nsamples"], resp, K, device=local)
+        t0 = time.perf_counter()
+        tab = calculate_antenna_array_response(pos, K, lam)
+        blkx.set_array_response(tab)
+        t_py = time.perf_counter() - t0
+        blkx.set_array_geometry(pos, lam)
+        ts = []
+        for i in range(5):
+            t0 = time.perf_counter()
+            guarded = blkx.set_array_geometry(pos, lam * (1.0 + 1e-3 * i))
+            ts.append(time.perf_counter() - t0)
+        same = bool(np.array_equal(blkx.array_response_c64().view(np.uint32),
+                                   np.asarray(calculate_antenna_array_response(pos, K, lam * (1.0 + 1e-3 * 4))).astype(np.complex64).view(np.uint32)))
+        blkx.close()
+        next_rows["retune"] = {"device_ms": 1e3 * sorted(ts)[2], "python_helper_ms": 1e3 * t_py, "entries": 2 * M * K,
+                               "guarded_entries": guarded, "table_bit_identical": same,
+                               "api": "music_b200_set_geometry vs calculate_antenna_array_response + set_array_response"}
+
     cpu = None
     if rank == 0 and G == 1 and not args.no_cpu_baseline:
         threads = host_threads()
@@ -426,7 +479,7 @@ def run_ours(args):
                        "sharding": "round-robin w mod G, NCCL all-gather of int32 peak bins" if G > 1 else "single GPU",
                        "snr_db": cfg["snr_db"], "geometry": cfg["geometry"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "stages": stages, "sanity_bins_within_2_of_truth": ok_frac,
+            "stages": stages, "sanity_bins_within_2_of_truth": ok_frac, "next_rows": next_rows,
         }
         print(json.dumps(line))
     blk.close()

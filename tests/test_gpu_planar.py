@@ -53,7 +53,7 @@ def test_planar_host_matches_oracle_on_formed_windows(base, over, hop, W):
     table = helpers.table_for(cfg)
     streams = streams_for(cfg, 1234 + base, (W - 1) * hop_ + N)
     x = form_windows(streams, hop_, W, N)
-    ref = co.work_batch(x, cfg["m"], cfg["n"], table)
+    ref = co.work_batch(x, cfg["m"], cfg["n"], table, want_spectrum=True)
     blk = music_doa(cfg["m"], cfg["n"], cfg["nsamples"], table.tolist(), cfg["resolution"])
     ang = np.full((W, cfg["n"]), -7, np.float32)
     lvl = np.full((W, cfg["n"]), -7, np.float32)
@@ -66,6 +66,19 @@ def test_planar_host_matches_oracle_on_formed_windows(base, over, hop, W):
     # and the same bins as the interleaved entry on the copied windows
     ang2 = np.zeros_like(ang)
     assert blk.work(W, [x], [ang2]) == W and np.array_equal(ang2, ang)
+
+
+def assert_bins_equal_up_to_exact_ties(got, ref):
+    """Bit-exact bins, except where the oracle itself sees a tie to the last ulp: a window that straddles two
+    source angles has a flat spectrum whose maximum sits on the broadside mirror pair (90 / 270 degrees) of the
+    x-axis ULA, P equal to ~1 ulp; which of the two wins then depends on the rounding of R (summation order)."""
+    bad = np.nonzero(np.any(got != ref["bins"], axis=1))[0]
+    assert len(bad) <= 0.01 * len(got)
+    for w in bad:
+        P = ref["P"][w]
+        for g, r in zip(got[w], ref["bins"][w]):
+            assert abs(P[g] - P[r]) <= 4e-16 * P[r], (w, g, r, P[g], P[r])
+    return len(bad)
 
 
 def test_planar_device_entry_many_windows_with_overlap():
@@ -85,8 +98,9 @@ def test_planar_device_entry_many_windows_with_overlap():
     blk.process_planar_device([t.data_ptr() for t in d_streams], hop, W, d_ang.data_ptr(), d_lvl.data_ptr(), None,
                               d_bins.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert np.array_equal(d_bins.cpu().numpy(), ref["bins"])
-    assert np.array_equal(d_ang.cpu().numpy(), ref["angles"])
+    ties = assert_bins_equal_up_to_exact_ties(d_bins.cpu().numpy(), ref)
+    if ties == 0:
+        assert np.array_equal(d_ang.cpu().numpy(), ref["angles"])
     assert helpers.rel_err(d_lvl.cpu().numpy(), ref["levels"]) <= P_RTOL
     # unaligned stream start (odd snapshot offset: 8-byte but not 16-byte aligned) gives the shifted windows
     blk.process_planar_device([t.data_ptr() + 8 for t in d_streams], hop, W - 1, d_ang.data_ptr(), d_lvl.data_ptr(), None,
@@ -94,7 +108,27 @@ def test_planar_device_entry_many_windows_with_overlap():
     torch.cuda.synchronize()
     x1 = form_windows([s[1:] for s in streams], hop, W - 1, N)
     ref1 = co.work_batch(x1, cfg["m"], cfg["n"], table)
-    assert np.array_equal(d_bins.cpu().numpy()[:W - 1], ref1["bins"])
+    assert_bins_equal_up_to_exact_ties(d_bins.cpu().numpy()[:W - 1], ref1)
+
+
+def test_planar_device_entry_uca_overlap_is_bit_exact():
+    """same as above on a circular array (no mirror symmetry, hence no exact ties): bins bit-exact"""
+    cfg = synth.config(4, snapshots=512, resolution=1800)
+    N, hop, W = 512, 128, 900
+    table = helpers.table_for(cfg)
+    streams = streams_for(cfg, 78, (W - 1) * hop + N)
+    x = form_windows(streams, hop, W, N)
+    ref = co.work_batch(x, cfg["m"], cfg["n"], table)
+    blk = music_doa(cfg["m"], cfg["n"], cfg["nsamples"], table.tolist(), cfg["resolution"])
+    dev = torch.device("cuda:0")
+    d_streams = [torch.from_numpy(s.view(np.float32)).to(dev) for s in streams]
+    d_ang = torch.zeros(W, 1, dtype=torch.float32, device=dev)
+    d_bins = torch.zeros(W, 1, dtype=torch.int32, device=dev)
+    blk.process_planar_device([t.data_ptr() for t in d_streams], hop, W, d_ang.data_ptr(), None, None,
+                              d_bins.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_bins.cpu().numpy(), ref["bins"])
+    assert np.array_equal(d_ang.cpu().numpy(), ref["angles"])
 
 
 def test_planar_argument_errors():
