@@ -428,7 +428,7 @@ def run_ours(args):
         next_rows = {}
         N, M = cfg["snapshots"], cfg["m"]
         # (f2) planar antenna streams: the same samples as d_in, de-interleaved once (setup, untimed)
-        Wp = min(W, 4096)
+        Wp = W
         planar = d_in[:Wp].view(Wp, N, M, 2).permute(2, 0, 1, 3).contiguous().view(M, Wp * N * 2)
         ptrs = [planar[r].data_ptr() for r in range(M)]
         d_bp = torch.empty((2 * Wp, n), dtype=torch.int32, device=dev)

@@ -425,16 +425,27 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
     if (nwindows == 0) return MUSIC_B200_OK;
     if ((!planar && !d_in) || !d_ang) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 and d_angles must not be NULL");
     if (!planar && (reinterpret_cast<uintptr_t>(d_in) & 15u) != 0) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 must be 16-byte aligned");
-    if (!planar && h->fused && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
+    // planar streams can take the fused path when the 16-byte granularity of bulk copies allows it
+    bool planar_fusable = false;
+    if (planar) {
+        planar_fusable = (hop % 2 == 0) && (h->N % 2 == 0);
+        for (uint32_t r = 0; r < h->m; ++r) planar_fusable = planar_fusable && (reinterpret_cast<uintptr_t>(planar->p[r]) & 15u) == 0;
+    }
+    if ((!planar || planar_fusable) && h->fused && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
         // whole call in one persistent launch (music_fused.cuh); no workspace involved
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
         const int grid = std::min<int>(h->sm_count, (int)((nwindows + FZ_COV_WARPS - 1) / FZ_COV_WARPS));
         if (h->fused_used) CU(h, cudaStreamWaitEvent(st, h->fused_done, 0));
         const DeviceTable &tb = h->table[h->cur_table];
-        music4_fused_kernel<<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, tb.fz, tb.c64, tb.na_max, (int)nwindows, (int)h->N,
-                                                             (int)h->K, PeakOut{d_ang, d_lvl, d_bins}, h->work_ctr,
-                                                             h->fused_trace);
+        if (planar)
+            music4_fused_kernel<true><<<grid, FZ_THREADS, FZ_SMEM, st>>>(nullptr, *planar, 0ull, hop, tb.fz, tb.c64, tb.na_max, (int)nwindows,
+                                                                         (int)h->N, (int)h->K, PeakOut{d_ang, d_lvl, d_bins},
+                                                                         h->work_ctr, h->fused_trace);
+        else
+            music4_fused_kernel<false><<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, PlanarStreams{}, 0ull, 0u, tb.fz, tb.c64, tb.na_max,
+                                                                          (int)nwindows, (int)h->N, (int)h->K,
+                                                                          PeakOut{d_ang, d_lvl, d_bins}, h->work_ctr, h->fused_trace);
         h->launches++;
         CU(h, cudaEventRecord(h->fused_done, st));
         h->fused_used = true;
@@ -640,7 +651,8 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
             CU(h, cudaMalloc(&h->fused_trace, 16 * sizeof(long long) * 1024));
             CU(h, cudaMemset(h->fused_trace, 0, 16 * sizeof(long long) * 1024));
         }
-        CU(h, cudaFuncSetAttribute(music4_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
+        CU(h, cudaFuncSetAttribute(music4_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
+        CU(h, cudaFuncSetAttribute(music4_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 6 * COV_CHUNK));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 4 * COV_CHUNK));
         return upload_table(h, 0, table_c64, h->streams[0]);

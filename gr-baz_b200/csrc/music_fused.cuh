@@ -34,6 +34,7 @@
 // window except the optional spectrum port).
 #pragma once
 #include "music_kernels.cuh"
+#include "music_planar.cuh"
 
 namespace music {
 
@@ -165,8 +166,14 @@ __device__ __forceinline__ double fused_exact_P(const float *__restrict__ tab_c6
     return 1.0 / d;
 }
 
+// PLANAR = true: the window is read from four per-antenna streams (music_planar.cuh) - window w = snapshots
+// [first_snapshot + w * hop, ... + N) of each stream - by four 1 KiB bulk copies per stage instead of one 4 KiB copy;
+// the stage then holds [antenna][128 snapshots] and a lane gathers its snapshot with four LDS.64.  Requires 16-byte
+// aligned streams and even first_snapshot, hop and N (bulk copies move multiples of 16 bytes).
+template <bool PLANAR>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
-music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restrict__ tbl /* fused_table_bytes(K) */,
+music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigned long long first_snapshot, unsigned hop,
+                    const unsigned char *__restrict__ tbl /* fused_table_bytes(K) */,
                     const float *__restrict__ tab_c64 /* [K][4] complex64 */, const float *__restrict__ na_max_p, int W, int N,
                     int K, PeakOut out, unsigned *__restrict__ work_ctr /* [0]: window tickets, [1]: finished CTAs; both zero between launches */,
                     long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */)
@@ -226,9 +233,15 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
             if (iw < 0) return;
             const size_t off = (size_t)iq * COV_CHUNK;
             const uint32_t bytes = (uint32_t)min((size_t)COV_CHUNK, win_bytes - off);
-            const unsigned char *src = src0 + (size_t)iw * win_bytes + off;
             mbar_expect_tx(bar0 + 8 * islot, bytes);
-            bulk_g2s(ring0 + islot * COV_CHUNK, src, bytes, bar0 + 8 * islot);
+            if (PLANAR) {
+                const unsigned long long s0 = first_snapshot + (unsigned long long)iw * hop + (unsigned long long)iq * (COV_CHUNK / 32);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    bulk_g2s(ring0 + islot * COV_CHUNK + r * (COV_CHUNK / 4), S.p[r] + s0, bytes / 4, bar0 + 8 * islot);
+            } else {
+                bulk_g2s(ring0 + islot * COV_CHUNK, src0 + (size_t)iw * win_bytes + off, bytes, bar0 + 8 * islot);
+            }
             if (++islot == FZ_STAGES) islot = 0;
             if (++iq == cpw) { iq = 0; claim(); }
         };
@@ -250,17 +263,29 @@ music4_fused_kernel(const float *__restrict__ in, const unsigned char *__restric
                 const size_t off = (size_t)q * COV_CHUNK;
                 const int nsnap = (int)(min((size_t)COV_CHUNK, win_bytes - off) >> 5);
                 const float4 *buf = reinterpret_cast<const float4 *>(ring + (size_t)slot * COV_CHUNK);
+                const float2 *pbuf = reinterpret_cast<const float2 *>(buf);  // PLANAR: [antenna][COV_CHUNK / 32 snapshots]
+                auto snap = [&](int s, float4 &a, float4 &b) {
+                    if (PLANAR) {
+                        const float2 x0 = pbuf[s], x1 = pbuf[COV_CHUNK / 32 + s], x2 = pbuf[2 * (COV_CHUNK / 32) + s], x3 = pbuf[3 * (COV_CHUNK / 32) + s];
+                        a = make_float4(x0.x, x0.y, x1.x, x1.y);
+                        b = make_float4(x2.x, x2.y, x3.x, x3.y);
+                    } else {
+                        a = buf[2 * s];
+                        b = buf[2 * s + 1];
+                    }
+                };
                 if (nsnap == COV_CHUNK / 32) {
                     float4 xa[4], xb[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        xa[u] = buf[2 * (lane + 32 * u)];
-                        xb[u] = buf[2 * (lane + 32 * u) + 1];
-                    }
+                    for (int u = 0; u < 4; ++u) snap(lane + 32 * u, xa[u], xb[u]);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) cov4_accumulate(acc, xa[u], xb[u]);
                 } else {
-                    for (int s = lane; s < nsnap; s += 32) cov4_accumulate(acc, buf[2 * s], buf[2 * s + 1]);
+                    for (int s = lane; s < nsnap; s += 32) {
+                        float4 a, b;
+                        snap(s, a, b);
+                        cov4_accumulate(acc, a, b);
+                    }
                 }
                 __syncwarp();  // every lane is done reading the slot -> it may be refilled
                 if (lane == 0) issue();

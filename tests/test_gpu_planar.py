@@ -69,15 +69,17 @@ def test_planar_host_matches_oracle_on_formed_windows(base, over, hop, W):
 
 
 def assert_bins_equal_up_to_exact_ties(got, ref):
-    """Bit-exact bins, except where the oracle itself sees a tie to the last ulp: a window that straddles two
-    source angles has a flat spectrum whose maximum sits on the broadside mirror pair (90 / 270 degrees) of the
-    x-axis ULA, P equal to ~1 ulp; which of the two wins then depends on the rounding of R (summation order)."""
+    """Bit-exact bins, except where the oracle itself sees a tie inside fp64 noise.  On the x-axis ULA the broadside
+    mirror pair (90 / 270 degrees) has table rows that differ only in imaginary parts of ~1e-16, so P at the two
+    bins agrees to ~1e-14; P is conditioned ~4000x w.r.t. R, i.e. any fp64 implementation
+    (the reference's LAPACK path included) carries ~1e-12 of rounding noise in P, and which of the two bins wins
+    depends on the summation order of R.  Seen when a source sits at broadside or a window straddles two sources."""
     bad = np.nonzero(np.any(got != ref["bins"], axis=1))[0]
     assert len(bad) <= 0.01 * len(got)
     for w in bad:
         P = ref["P"][w]
         for g, r in zip(got[w], ref["bins"][w]):
-            assert abs(P[g] - P[r]) <= 4e-16 * P[r], (w, g, r, P[g], P[r])
+            assert abs(P[g] - P[r]) <= 1e-12 * P[r], (w, g, r, P[g], P[r])
     return len(bad)
 
 
@@ -109,6 +111,30 @@ def test_planar_device_entry_many_windows_with_overlap():
     x1 = form_windows([s[1:] for s in streams], hop, W - 1, N)
     ref1 = co.work_batch(x1, cfg["m"], cfg["n"], table)
     assert_bins_equal_up_to_exact_ties(d_bins.cpu().numpy()[:W - 1], ref1)
+
+
+@pytest.mark.parametrize("N,hop,W", [(1000, 1000, 300), (1000, 500, 300), (1024, 2, 260), (1000, 334, 120), (1000, 333, 120), (130, 64, 1100)])
+def test_planar_fused_path_m4(N, hop, W):
+    """M = 4, n = 1, peak outputs only: planar streams go through the fused persistent kernel (four 1 KiB bulk copies
+    per stage) when hop and N are even, else through cov_planar_kernel; both must match the oracle.  N = 1000 / 130
+    leave a partial last stage; W > 8 * 148 exercises the dynamic tickets."""
+    cfg = synth.config(2, snapshots=N, resolution=720)
+    table = helpers.table_for(cfg)
+    streams = streams_for(cfg, 4321 + hop, (W - 1) * hop + N)
+    x = form_windows(streams, hop, W, N)
+    ref = co.work_batch(x, cfg["m"], cfg["n"], table)
+    blk = music_doa(cfg["m"], cfg["n"], cfg["nsamples"], table.tolist(), cfg["resolution"])
+    ang = np.full((W, 1), -7, np.float32)
+    lvl = np.full((W, 1), -7, np.float32)
+    l0 = blk.launch_count()
+    assert blk.work_planar(W, streams, [ang, lvl], hop=hop) == W
+    launches = blk.launch_count() - l0
+    fusable = hop % 2 == 0 and N % 2 == 0
+    assert (launches <= 2) if fusable else (launches >= 3)  # one fused launch per host chunk vs cov + eig + scan
+    assert_bins_equal_up_to_exact_ties(blk.last_bins(), ref)
+    ok = np.all(blk.last_bins() == ref["bins"], axis=1)
+    assert np.array_equal(ang[ok], ref["angles"][ok])
+    assert helpers.rel_err(lvl[ok], ref["levels"][ok]) <= P_RTOL
 
 
 def test_planar_device_entry_uca_overlap_is_bit_exact():
