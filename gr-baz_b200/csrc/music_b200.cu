@@ -62,6 +62,8 @@ struct music_b200 {
     unsigned *steer_count = nullptr;
     int *steer_list = nullptr;
     float *steer_vals = nullptr;
+    int peak_mode = MUSIC_B200_PEAKS_TOP_BINS;  // set_peak_mode()
+    uint32_t peak_excl = 0;
     unsigned steer_guarded = 0;    // entries of the last built table re-evaluated with the host libm
 
     // fp64 workspace slots (R, eigenvalues, sorted eigenvectors, optional strengths) and the two
@@ -366,7 +368,8 @@ int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, float *d_ang
         h->launches++;
     }
     if (tev) cudaEventRecord(tev[2], st);
-    const bool argmax = (h->n == 1);
+    const bool local = h->peak_mode == MUSIC_B200_PEAKS_LOCAL_MAXIMA;
+    const bool argmax = (h->n == 1) && !local;
     const bool need_p64 = !argmax || d_P64_out != nullptr;
     double *p64 = d_P64_out ? d_P64_out : ws.P64;
     PeakOut po{d_ang, d_lvl, d_bins};
@@ -387,7 +390,8 @@ int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, float *d_ang
     }
     if (tev) cudaEventRecord(tev[3], st);
     if (!argmax) {
-        topn_kernel<<<(W + 7) / 8, 256, 0, st>>>(p64, (int)h->n, (int)h->K, (int)W, po);
+        if (local) topn_local_kernel<<<(W + 7) / 8, 256, 0, st>>>(p64, (int)h->n, (int)h->K, (int)W, (int)h->peak_excl, po);
+        else topn_kernel<<<(W + 7) / 8, 256, 0, st>>>(p64, (int)h->n, (int)h->K, (int)W, po);
         h->launches++;
     }
     if (tev) cudaEventRecord(tev[4], st);
@@ -431,7 +435,8 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         planar_fusable = (hop % 2 == 0) && (h->N % 2 == 0);
         for (uint32_t r = 0; r < h->m; ++r) planar_fusable = planar_fusable && (reinterpret_cast<uintptr_t>(planar->p[r]) & 15u) == 0;
     }
-    if ((!planar || planar_fusable) && h->fused && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
+    const bool local_peaks = h->peak_mode == MUSIC_B200_PEAKS_LOCAL_MAXIMA;
+    if ((!planar || planar_fusable) && h->fused && !local_peaks && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
         // whole call in one persistent launch (music_fused.cuh); no workspace involved
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
@@ -453,7 +458,7 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         CU(h, cudaGetLastError());
         return MUSIC_B200_OK;
     }
-    const bool internal_p64 = (h->n != 1) && !d_P64;
+    const bool internal_p64 = (h->n != 1 || local_peaks) && !d_P64;
     const uint32_t max_sub = max_sub_windows(h, internal_p64);
     const bool pipe = allow_pipeline && h->pipeline && !h->timing && nwindows >= 2 * MIN_SUB;
     uint32_t sub;
@@ -754,6 +759,17 @@ int music_b200_process_planar_host(music_b200 *h, const float *const *streams, u
     if (rc) return rc;
     if (e0 != cudaSuccess || e1 != cudaSuccess)
         return fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    return MUSIC_B200_OK;
+}
+
+int music_b200_set_peak_mode(music_b200 *h, int mode, uint32_t exclusion_bins)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (mode != MUSIC_B200_PEAKS_TOP_BINS && mode != MUSIC_B200_PEAKS_LOCAL_MAXIMA) return fail(h, MUSIC_B200_EINVAL, "unknown peak mode %d", mode);
+    if (exclusion_bins >= h->K) return fail(h, MUSIC_B200_EINVAL, "exclusion_bins must be < resolution");
+    std::lock_guard<std::mutex> g(h->mutex);
+    h->peak_mode = mode;
+    h->peak_excl = exclusion_bins;
     return MUSIC_B200_OK;
 }
 

@@ -1129,4 +1129,60 @@ __global__ void __launch_bounds__(256) topn_kernel(const double *__restrict__ P6
     }
 }
 
+// Opt-in peak rule (not in the reference; SURVEY.md section 8(f) rank 3, oracle/music_oracle.py::pick_local_maxima):
+// the n largest circular local maxima of P, at least `excl` + 1 bins apart.  One warp per window; pass r finds the
+// best remaining candidate (P[k] > 0, P[k] > P[k-1], P[k] >= P[k+1], farther than excl bins from every peak taken
+// so far; ties -> lowest k).
+__global__ void __launch_bounds__(256) topn_local_kernel(const double *__restrict__ P64, int n, int K, int W, int excl, PeakOut out)
+{
+    __shared__ int taken_all[8][MAXM];  // per warp: bins of the picks made so far
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= W) return;
+    volatile int *taken = taken_all[threadIdx.x >> 5];
+    const double *P = P64 + (size_t)w * K;
+    bool dry = false;
+    for (int r = 0; r < n; ++r) {
+        double bP = 0.0;
+        int bk = -1;
+        if (!dry) {
+            for (int k = lane; k < K; k += 32) {
+                const double p = P[k];
+                if (!(p > 0.0) || !(p > bP)) continue;  // also skips NaN; an equal p at a higher k never wins
+                const double pl = P[k == 0 ? K - 1 : k - 1], pr = P[k == K - 1 ? 0 : k + 1];
+                if (!(p > pl) || !(p >= pr)) continue;
+                bool ok = true;
+                for (int q = 0; q < r; ++q) {
+                    const int t = taken[q];
+                    int d = k > t ? k - t : t - k;
+                    d = min(d, K - d);
+                    ok = ok && d > excl;
+                }
+                if (ok) { bP = p; bk = k; }
+            }
+        }
+        __syncwarp();  // lanes leave the k loop after different trip counts
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double Po = __shfl_xor_sync(0xffffffffu, bP, o);
+            const int ko = __shfl_xor_sync(0xffffffffu, bk, o);
+            if (peak_better(Po, ko, bP, bk)) { bP = Po; bk = ko; }
+        }
+        if (bk < 0) dry = true;
+        if (lane == 0) {
+            if (r < MAXM) taken[r] = bk;
+            const size_t o = (size_t)w * n + r;
+            if (bk >= 0) {
+                out.angles[o] = (float)((double)bk * 360.0 / (double)K);
+                if (out.levels) out.levels[o] = (float)bP;
+            } else {
+                out.angles[o] = 0.f;
+                if (out.levels) out.levels[o] = 0.f;
+            }
+            if (out.bins) out.bins[o] = bk;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace music

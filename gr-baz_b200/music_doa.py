@@ -91,6 +91,15 @@ class music_doa(object):
         _capi.check(self._lib.music_b200_set_geometry(self._h, pos.ctypes.data, float(l), ctypes.byref(guarded)), self._h)
         return int(guarded.value)
 
+    # -- extension: opt-in local-maximum peak rule --------------
+    def set_peak_mode(self, mode="top_bins", exclusion_bins=0):
+        """``"top_bins"`` (default) = the reference's rule (/root/reference/lib/baz_music_doa.cc:129-141);
+        ``"local_maxima"`` = the n largest circular local maxima more than ``exclusion_bins`` apart."""
+        modes = {"top_bins": 0, "local_maxima": 1}
+        if mode not in modes:
+            raise ValueError("mode must be one of %s" % sorted(modes))
+        _capi.check(self._lib.music_b200_set_peak_mode(self._h, modes[mode], int(exclusion_bins)), self._h)
+
     def array_response_c64(self):
         """The table in use, as complex64 (resolution, m) - what the block holds after the SWIG
         conversion (swig/baz_swig.i:564)."""

@@ -63,6 +63,18 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
 int music_b200_set_table(music_b200 *h, const float *table_c64);
 
 /*
+ * Peak rule.  MUSIC_B200_PEAKS_TOP_BINS (default) is the reference's: the n largest bins, ties to the
+ * lower bin (/root/reference/lib/baz_music_doa.cc:129-141) - for n >= 2 usually neighbouring bins of one
+ * peak.  MUSIC_B200_PEAKS_LOCAL_MAXIMA is an opt-in extension with no reference counterpart: the n
+ * largest circular local maxima (P[k] > P[k-1] and P[k] >= P[k+1], P[k] > 0), each more than
+ * exclusion_bins away from every stronger peak taken; outputs in descending strength, unfilled slots
+ * (0, 0, bin -1).  Applies to later process_*() calls.
+ */
+#define MUSIC_B200_PEAKS_TOP_BINS 0
+#define MUSIC_B200_PEAKS_LOCAL_MAXIMA 1
+int music_b200_set_peak_mode(music_b200 *h, int mode, uint32_t exclusion_bins);
+
+/*
  * Planar input: one c64 stream per antenna instead of interleaved items.  Window w is
  *     x_w(r, c) = streams[r][w * hop + c],   r < m, c < N = nsamples / m,
  * i.e. what the flowgraph in front of the reference block builds on the CPU by interleaving the

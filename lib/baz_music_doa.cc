@@ -110,6 +110,14 @@ void baz_music_doa::set_array_geometry(const std::vector<std::vector<double> > &
     if (rc != MUSIC_B200_OK) throw std::runtime_error(std::string("music_doa: ") + music_b200_last_error(d_handle));
 }
 
+/* Extension (not in the reference): opt-in local-maximum peak rule, see include/music_b200.h. */
+void baz_music_doa::set_peak_mode(int mode, unsigned int exclusion_bins)
+{
+    gr::thread::scoped_lock guard(d_mutex);
+    const int rc = music_b200_set_peak_mode(d_handle, mode, exclusion_bins);
+    if (rc != MUSIC_B200_OK) throw std::invalid_argument(std::string("music_doa: ") + music_b200_last_error(d_handle));
+}
+
 int baz_music_doa::work(int noutput_items, gr_vector_const_void_star &input_items, gr_vector_void_star &output_items)
 {
     if (noutput_items <= 0) return 0;

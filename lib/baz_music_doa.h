@@ -51,6 +51,8 @@ public:
     void set_array_response(const array_response_t &array_response);
     /* extension: device-side table build from element positions [m][x, y] (metres) and the wavelength */
     void set_array_geometry(const std::vector<std::vector<double> > &positions_xy, double wavelength);
+    /* extension: 0 = the reference's n largest bins (default), 1 = n largest local maxima > exclusion_bins apart */
+    void set_peak_mode(int mode, unsigned int exclusion_bins);
 
     /* Integer peak-bin indices of the items produced by the last work() call, [items][n]
      * (not in the reference; -1 marks a slot the reference would leave at (0, 0)). */

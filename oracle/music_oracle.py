@@ -118,6 +118,32 @@ def pick_top_n(P, n, resolution):
     return out
 
 
+def pick_local_maxima(P, n, resolution, exclusion=0):
+    """NOT in the reference (opt-in): the reference's rule (:129-141) returns the n
+    largest BINS, which for n >= 2 are usually neighbours on the flank of one peak.  This mode returns the n
+    largest circular LOCAL MAXIMA instead.  Definition (ours - there is no reference behaviour to match):
+      * bin k is a candidate iff P[k] > 0, P[k] > P[k-1] and P[k] >= P[k+1] (indices mod K; NaN compares false;
+        on a plateau only the lowest bin qualifies);
+      * repeat n times: take the candidate with the largest P (ties: lowest k) whose circular distance to every
+        peak already taken is > exclusion bins;
+      * output order = pick order (strength descending); unfilled slots stay (0, 0, -1) like the reference's
+        initial pairs (:95)."""
+    P = np.asarray(P, dtype=np.float64)
+    K = int(resolution)
+    with np.errstate(invalid="ignore"):
+        cand = np.nonzero((P > 0.0) & (P > np.roll(P, 1)) & (P >= np.roll(P, -1)))[0]
+    order = cand[np.lexsort((cand, -P[cand]))]
+    taken = []
+    for k in order:
+        if len(taken) == n:
+            break
+        if all(min((k - t) % K, (t - k) % K) > exclusion for t in taken):
+            taken.append(int(k))
+    out = [(float(k) * 360.0 / float(K), float(P[k]), int(k)) for k in taken]
+    out += [(0.0, 0.0, -1)] * (n - len(out))
+    return out
+
+
 def work(in_c64, m, n, table_c64, want_spectrum=True, literal_pick=False, return_internals=False):
     """One window through lib/baz_music_doa.cc:72-161.
 

@@ -31,6 +31,7 @@ private:
 public:
 	void set_array_response(const std::vector<std::vector<gr_complex> >& array_response);
 	void set_array_geometry(const std::vector<std::vector<double> >& positions_xy, double wavelength);
+	void set_peak_mode(int mode, unsigned int exclusion_bins);
 };
 
 #endif // MUSIC_B200_FOUND

@@ -136,3 +136,19 @@ def test_angle_is_injective_in_float32():
     for K in (360, 3600, 7200):
         ang = (np.arange(K) * 360.0 / K).astype(np.float32)
         assert np.array_equal(np.rint(ang.astype(np.float64) * K / 360.0).astype(np.int64), np.arange(K))
+
+
+def test_pick_local_maxima_rule():
+    """the opt-in peak rule (not in the reference): definition checks on hand-made spectra"""
+    K = 12
+    P = np.array([1, 5, 5, 2, 1, 9, 3, 3, 7, 1, 0.5, 4], np.float64)
+    # local maxima: k=1 (plateau 5,5 -> lowest bin), k=5, k=8, k=11 (4 > 0.5 and 4 >= P[0]=1, circular)
+    got = mo.pick_local_maxima(P, 4, K)
+    assert [g[2] for g in got] == [5, 8, 1, 11]
+    assert got[0][0] == 5 * 360.0 / K and got[0][1] == 9.0
+    # exclusion: 8 is 3 bins from 5 -> dropped with exclusion 3; 1 is 4 away -> kept; 11 is 2 from 1 (circular) -> dropped
+    assert [g[2] for g in mo.pick_local_maxima(P, 4, K, exclusion=3)] == [5, 1, -1, -1]
+    assert [g[2] for g in mo.pick_local_maxima(P, 2, K, exclusion=0)] == [5, 8]
+    # NaN and non-positive bins are never candidates and never beat a neighbour
+    Q = P.copy(); Q[5] = np.nan; Q[8] = 0.0
+    assert [g[2] for g in mo.pick_local_maxima(Q, 3, K)] == [1, 11, 9]  # bin 6 fails 3 > NaN; bin 9 (1 > 0, 1 >= 0.5) qualifies
