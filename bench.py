@@ -416,10 +416,23 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the PCIe roof of this leg: the same host buffer copied to the device and nothing else
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d_tmp = d_in[:We]  # h_in holds exactly these windows: the copy does not change the data
+        for _ in range(2):
+            d_tmp.copy_(h_in, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record(stream)
+        for _ in range(3):
+            d_tmp.copy_(h_in, non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * We * cfg["nsamples"] * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         e2e = {"value": We * G * esteps / dt, "unit": "windows/s",
                "h2d_bytes_per_step": int(We * cfg["nsamples"] * 8),
                "d2h_bytes_per_step": int(We * n * 4 * 3), "windows_per_step": We, "steps": esteps,
-               "api": "music_doa.work() -> music_b200_process_host (pinned host buffers)"}
+               "api": "music_doa.work() -> music_b200_process_host (pinned host buffers)",
+               "h2d_copy_only_gbs": h2d_gbs, "e2e_input_gbs": We * esteps * cfg["nsamples"] * 8 / dt / 1e9}
         assert np.array_equal(blk.last_bins(), bins_h[:We]), "host path and device path disagree"
 
     # ---- SURVEY 8(f) rows built so far, same workload (untimed w.r.t. the headline; rank 0, N = 1) ----------
