@@ -91,6 +91,11 @@ struct music_b200 {
     float *d_in[2] = {nullptr, nullptr};
     float *d_ang[2] = {nullptr, nullptr}, *d_lvl[2] = {nullptr, nullptr}, *d_spec[2] = {nullptr, nullptr};
     int32_t *d_bins[2] = {nullptr, nullptr};
+    // pinned host mirrors of d_ang/d_lvl/d_bins: device->host copies into caller memory would be synchronous when that
+    // memory is pageable (numpy arrays, GNU Radio buffers) and stall the enqueue of the next chunk's upload
+    float *p_ang[2] = {nullptr, nullptr}, *p_lvl[2] = {nullptr, nullptr};
+    int32_t *p_bins[2] = {nullptr, nullptr};
+    uint32_t slot_w0[2] = {0, 0}, slot_W[2] = {0, 0};
     uint32_t host_chunk = 0;
     bool host_spec_alloc = false;
 };
@@ -508,8 +513,12 @@ void free_host_staging(music_b200 *h)
 {
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->d_in[i]); cudaFree(h->d_ang[i]); cudaFree(h->d_lvl[i]); cudaFree(h->d_spec[i]); cudaFree(h->d_bins[i]);
+        cudaFreeHost(h->p_ang[i]); cudaFreeHost(h->p_lvl[i]); cudaFreeHost(h->p_bins[i]);
         h->d_in[i] = h->d_ang[i] = h->d_lvl[i] = h->d_spec[i] = nullptr;
         h->d_bins[i] = nullptr;
+        h->p_ang[i] = h->p_lvl[i] = nullptr;
+        h->p_bins[i] = nullptr;
+        h->slot_W[i] = 0;
     }
     h->host_chunk = 0;
     h->host_spec_alloc = false;
@@ -525,12 +534,39 @@ int ensure_host_staging(music_b200 *h, uint32_t chunk, bool spec)
         CU(h, cudaMalloc(&h->d_ang[i], (size_t)cap * h->n * sizeof(float)));
         CU(h, cudaMalloc(&h->d_lvl[i], (size_t)cap * h->n * sizeof(float)));
         CU(h, cudaMalloc(&h->d_bins[i], (size_t)cap * h->n * sizeof(int32_t)));
+        CU(h, cudaHostAlloc(&h->p_ang[i], (size_t)cap * h->n * sizeof(float), cudaHostAllocDefault));
+        CU(h, cudaHostAlloc(&h->p_lvl[i], (size_t)cap * h->n * sizeof(float), cudaHostAllocDefault));
+        CU(h, cudaHostAlloc(&h->p_bins[i], (size_t)cap * h->n * sizeof(int32_t), cudaHostAllocDefault));
         if (spec) CU(h, cudaMalloc(&h->d_spec[i], (size_t)cap * h->K * sizeof(float)));
     }
     h->host_chunk = cap;
     h->host_spec_alloc = spec;
     return MUSIC_B200_OK;
 }
+
+// results of the chunk last computed in staging slot s: pinned mirror -> caller memory (the slot's stream is idle)
+void flush_host_slot(music_b200 *h, int s, float *angles, float *levels, int32_t *bins)
+{
+    const uint32_t W = h->slot_W[s];
+    if (!W) return;
+    const size_t off = (size_t)h->slot_w0[s] * h->n, cnt = (size_t)W * h->n;
+    memcpy(angles + off, h->p_ang[s], cnt * sizeof(float));
+    if (levels) memcpy(levels + off, h->p_lvl[s], cnt * sizeof(float));
+    if (bins) memcpy(bins + off, h->p_bins[s], cnt * sizeof(int32_t));
+    h->slot_W[s] = 0;
+}
+
+// device -> pinned mirrors of slot s (asynchronous on st whatever memory the caller's outputs live in)
+int download_host_slot(music_b200 *h, int s, uint32_t w0, uint32_t W, bool levels, bool bins, cudaStream_t st)
+{
+    CU(h, cudaMemcpyAsync(h->p_ang[s], h->d_ang[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (levels) CU(h, cudaMemcpyAsync(h->p_lvl[s], h->d_lvl[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (bins) CU(h, cudaMemcpyAsync(h->p_bins[s], h->d_bins[s], (size_t)W * h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    h->slot_w0[s] = w0;
+    h->slot_W[s] = W;
+    return MUSIC_B200_OK;
+}
+
 
 }  // namespace
 
@@ -737,7 +773,10 @@ int music_b200_process_planar_host(music_b200 *h, const float *const *streams, u
         const int s = it & 1;
         const uint32_t W = std::min(chunk, nwindows - w0);
         cudaStream_t st = h->streams[s];
-        if (it >= 2) CU(h, cudaStreamSynchronize(st));
+        if (it >= 2) {
+            CU(h, cudaStreamSynchronize(st));
+            flush_host_slot(h, s, angles, levels, bins);
+        }
         const size_t seg = (size_t)(W - 1) * hop + N;  // snapshots of each stream this chunk touches
         PlanarStreams S;
         for (uint32_t r = 0; r < MAXM; ++r) S.p[r] = nullptr;
@@ -749,16 +788,18 @@ int music_b200_process_planar_host(music_b200 *h, const float *const *streams, u
         rc = enqueue_device(h, nullptr, W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
                             nullptr, nullptr, nullptr, st, s, false, &S, hop);
         if (rc) break;
-        CU(h, cudaMemcpyAsync(angles + (size_t)w0 * h->n, h->d_ang[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (levels) CU(h, cudaMemcpyAsync(levels + (size_t)w0 * h->n, h->d_lvl[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (bins) CU(h, cudaMemcpyAsync(bins + (size_t)w0 * h->n, h->d_bins[s], (size_t)W * h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        rc = download_host_slot(h, s, w0, W, levels != nullptr, bins != nullptr, st);
+        if (rc) break;
         if (spectrum) CU(h, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
     cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    if (rc || e0 != cudaSuccess || e1 != cudaSuccess) h->slot_W[0] = h->slot_W[1] = 0;  // nothing valid to hand out
     if (rc) return rc;
     if (e0 != cudaSuccess || e1 != cudaSuccess)
         return fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    flush_host_slot(h, 0, angles, levels, bins);
+    flush_host_slot(h, 1, angles, levels, bins);
     return MUSIC_B200_OK;
 }
 
@@ -848,21 +889,26 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
         const int s = it & 1;
         const uint32_t W = std::min(chunk, nwindows - w0);
         cudaStream_t st = h->streams[s];
-        if (it >= 2) CU(h, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
+        if (it >= 2) {
+            CU(h, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
+            flush_host_slot(h, s, angles, levels, bins);
+        }
         CU(h, cudaMemcpyAsync(h->d_in[s], in_c64 + (size_t)w0 * h->nsamples * 2, (size_t)W * win_bytes, cudaMemcpyHostToDevice, st));
         rc = enqueue_device(h, h->d_in[s], W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
                             nullptr, nullptr, nullptr, st, s, false);
         if (rc) break;
-        CU(h, cudaMemcpyAsync(angles + (size_t)w0 * h->n, h->d_ang[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (levels) CU(h, cudaMemcpyAsync(levels + (size_t)w0 * h->n, h->d_lvl[s], (size_t)W * h->n * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (bins) CU(h, cudaMemcpyAsync(bins + (size_t)w0 * h->n, h->d_bins[s], (size_t)W * h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        rc = download_host_slot(h, s, w0, W, levels != nullptr, bins != nullptr, st);
+        if (rc) break;
         if (spectrum) CU(h, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
     cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    if (rc || e0 != cudaSuccess || e1 != cudaSuccess) h->slot_W[0] = h->slot_W[1] = 0;  // nothing valid to hand out
     if (rc) return rc;
     if (e0 != cudaSuccess || e1 != cudaSuccess)
         return fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    flush_host_slot(h, 0, angles, levels, bins);
+    flush_host_slot(h, 1, angles, levels, bins);
     return MUSIC_B200_OK;
 }
 
