@@ -75,6 +75,7 @@ struct music_b200 {
     unsigned *work_ctr = nullptr;      // fused kernel: [0] window tickets, [1] finished CTAs (self-resetting)
     cudaEvent_t fused_done = nullptr;  // launches of one handle are serialised (they share work_ctr)
     bool fused_used = false;
+    bool eig_coop = true;             // MUSIC_B200_EIG4=lane selects the one-lane-per-window eigensolver in the fused kernel
     long long *fused_trace = nullptr;  // MUSIC_B200_TRACE=1: per-CTA clock64 trace of the fused kernel (tools/fused_trace.py)
     bool fused = true;       // MUSIC_B200_FUSED=0 forces the three-kernel path
     bool covn = true;        // MUSIC_B200_COVN=0: M = 8/16 covariance by the v1 LDG tile kernels
@@ -451,11 +452,11 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         if (planar)
             music4_fused_kernel<true><<<grid, FZ_THREADS, FZ_SMEM, st>>>(nullptr, *planar, 0ull, hop, tb.fz, tb.c64, tb.na_max, (int)nwindows,
                                                                          (int)h->N, (int)h->K, PeakOut{d_ang, d_lvl, d_bins},
-                                                                         h->work_ctr, h->fused_trace);
+                                                                         h->work_ctr, h->fused_trace, h->eig_coop ? 1 : 0);
         else
             music4_fused_kernel<false><<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, PlanarStreams{}, 0ull, 0u, tb.fz, tb.c64, tb.na_max,
                                                                           (int)nwindows, (int)h->N, (int)h->K,
-                                                                          PeakOut{d_ang, d_lvl, d_bins}, h->work_ctr, h->fused_trace);
+                                                                          PeakOut{d_ang, d_lvl, d_bins}, h->work_ctr, h->fused_trace, h->eig_coop ? 1 : 0);
         h->launches++;
         CU(h, cudaEventRecord(h->fused_done, st));
         h->fused_used = true;
@@ -683,6 +684,7 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         if (const char *e = getenv("MUSIC_B200_SCAN")) h->scan_fast = strcmp(e, "general") != 0;
         if (const char *e = getenv("MUSIC_B200_FUSED")) h->fused = atoi(e) != 0;
         if (const char *e = getenv("MUSIC_B200_COVN")) h->covn = atoi(e) != 0;
+        if (const char *e = getenv("MUSIC_B200_EIG4")) h->eig_coop = strcmp(e, "lane") != 0;
         CU(h, cudaFuncSetAttribute(covN_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
         CU(h, cudaFuncSetAttribute(covN_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
         CU(h, cudaEventCreateWithFlags(&h->fused_done, cudaEventDisableTiming));

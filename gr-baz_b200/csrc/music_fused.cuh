@@ -176,7 +176,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     const unsigned char *__restrict__ tbl /* fused_table_bytes(K) */,
                     const float *__restrict__ tab_c64 /* [K][4] complex64 */, const float *__restrict__ na_max_p, int W, int N,
                     int K, PeakOut out, unsigned *__restrict__ work_ctr /* [0]: window tickets, [1]: finished CTAs; both zero between launches */,
-                    long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */)
+                    long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */,
+                    const int eig_coop /* 1: four lanes per window in the eigensolver warp, 0: one lane per window */)
 {
     const long long t_start = clock64();
     unsigned long long g_start = 0;
@@ -321,8 +322,11 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         }
-        if (lane == 0) atomicAdd((unsigned *)&ctl->cov_finished, 1u);
-        if (dbg && lane == 0 && warp < 2) dbg[blockIdx.x * 16 + warp] = clock64() - t_start;
+        if (lane == 0) {
+            const unsigned fin = atomicAdd((unsigned *)&ctl->cov_finished, 1u);
+            if (dbg && fin == (unsigned)FZ_COV_WARPS - 1) dbg[blockIdx.x * 16 + 0] = clock64() - t_start;  // last covariance warp
+            if (dbg && fin == 0) dbg[blockIdx.x * 16 + 1] = clock64() - t_start;                           // first one
+        }
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0;
@@ -336,10 +340,20 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             }
             __threadfence_block();
             const long long t0 = clock64();
-            const unsigned cnt = min(avail, 32u);
-            if ((unsigned)lane < cnt) {
-                const unsigned slot = (done + lane) % FZ_Q;
-                herm_eig_body<4, true>(Rq + (size_t)slot * 32, nullptr, Vq + (size_t)slot * 32, 4);
+            unsigned cnt;
+            if (eig_coop) {
+                // four lanes per window, 8 windows per round: a third of the one-lane solver's latency, and that
+                // latency is what the last windows of a launch wait for
+                cnt = min(avail, 8u);
+                const unsigned grp = (unsigned)lane >> 2;
+                const unsigned slot = (done + min(grp, cnt - 1)) % FZ_Q;
+                herm_eig4_coop(Rq + (size_t)slot * 32, Vq + (size_t)slot * 32, grp < cnt, lane & 3);
+            } else {
+                cnt = min(avail, 32u);
+                if ((unsigned)lane < cnt) {
+                    const unsigned slot = (done + lane) % FZ_Q;
+                    herm_eig_body<4, true>(Rq + (size_t)slot * 32, nullptr, Vq + (size_t)slot * 32, 4);
+                }
             }
             __syncwarp();
             __threadfence_block();

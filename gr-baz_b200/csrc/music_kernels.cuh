@@ -407,47 +407,80 @@ __device__ __forceinline__ bool eig_before(double wl, int l, double wj, int j)
 // rotations of a parallel-ordering step are one basic block and their dependent chains
 // interleave.  The eigensolver is latency-bound (one lane per window), and in the fused kernel
 // its latency is the pipeline's tail.
+// The rotation arithmetic of the M = 4 solvers, written with explicit rounding intrinsics so that the one-lane solver
+// (herm_eig_body<4, true>) and the four-lanes-per-window solver of the fused kernel (herm_eig4_coop) round identically
+// whatever the compiler would contract: their eigenvectors are bit-identical (tests compare the two paths exactly).
+__device__ __forceinline__ void jrot_params(const double gr, const double gi, const double app, const double aqq, double &c,
+                                            double &swr, double &swi, double &t, double &g)
+{
+    const double gg = fma(gr, gr, __dmul_rn(gi, gi));
+    const bool nz = gg > 0.0;                                  // false for 0 and NaN (NaN then propagates via g)
+    const double rg = nz ? rsqrt(gg) : 0.0;                    // 1 / |a_pq|
+    g = (gg != gg) ? gg : __dmul_rn(gg, rg);                   // |a_pq| (NaN stays NaN)
+    const double er = __dmul_rn(gr, rg), ei = __dmul_rn(gi, rg);
+    double theta = __dmul_rn(__dmul_rn(0.5, __dsub_rn(aqq, app)), rg);
+    theta = fmin(fmax(theta, -1e150), 1e150);                  // keeps theta^2 finite; |t| ~ 1/(2|theta|) ~ 0 there
+    const double q1 = fma(theta, theta, 1.0);
+    const double sq = __dmul_rn(q1, rsqrt(q1));                // sqrt(theta^2 + 1)
+    t = __ddiv_rn(1.0, __dadd_rn(fabs(theta), sq));
+    t = nz ? copysign(t, theta) : 0.0;
+    c = rsqrt(fma(t, t, 1.0));
+    const double sn = __dmul_rn(t, c);
+    swr = __dmul_rn(sn, er);                                   // s * e,  e = a_pq / |a_pq|
+    swi = __dmul_rn(sn, ei);
+}
+
+// (kp, kq) -> (c kp - conj(sw) kq, c kq + sw kp)
+__device__ __forceinline__ void jrot_mix(const double c, const double swr, const double swi, const double kpr, const double kpi,
+                                         const double kqr, const double kqi, double &npr, double &npi, double &nqr, double &nqi)
+{
+    npr = fma(c, kpr, -fma(swr, kqr, __dmul_rn(swi, kqi)));
+    npi = fma(c, kpi, -fma(swr, kqi, __dmul_rn(-swi, kqr)));
+    nqr = fma(c, kqr, fma(swr, kpr, __dmul_rn(-swi, kpi)));
+    nqi = fma(c, kqi, fma(swr, kpi, __dmul_rn(swi, kpr)));
+}
+
+// one half of jrot_mix with the same roundings: isq ? (c own + sw mate) : (c own - conj(sw) mate)
+__device__ __forceinline__ void jrot_mix_half(const double c, const double swr, const double swi, const bool isq, const double ownr,
+                                              const double owni, const double mr, const double mi, double &re, double &im)
+{
+    const double se = isq ? -swi : swi;
+    const double inr = fma(swr, mr, __dmul_rn(se, mi));
+    const double ini = fma(swr, mi, __dmul_rn(-se, mr));
+    re = fma(c, ownr, isq ? inr : -inr);
+    im = fma(c, owni, isq ? ini : -ini);
+}
+
+// eigenvector component times the phase that makes component 0 real
+__device__ __forceinline__ void eig_out4(const double vr, const double vi, const double pr, const double pi, double &re, double &im)
+{
+    re = fma(vr, pr, -__dmul_rn(vi, pi));
+    im = fma(vr, pi, __dmul_rn(vi, pr));
+}
+
 template <int MA>
 __device__ __forceinline__ void jacobi_rotate_bf(double (&Ar)[MA][MA], double (&Ai)[MA][MA], double (&Vr)[MA][MA],
                                                  double (&Vi)[MA][MA], const int p, const int q)
 {
-    const double gr = Ar[p][q], gi = Ai[p][q];
-    const double gg = fma(gr, gr, gi * gi);
-    const bool nz = gg > 0.0;                      // false for 0 and NaN (NaN then propagates via g)
-    const double rg = nz ? rsqrt(gg) : 0.0;        // 1 / |a_pq|
-    const double g = (gg != gg) ? gg : gg * rg;    // |a_pq| (NaN stays NaN)
     const double app = Ar[p][p], aqq = Ar[q][q];
-    const double er = gr * rg, ei = gi * rg;
-    double theta = 0.5 * (aqq - app) * rg;
-    theta = fmin(fmax(theta, -1e150), 1e150);      // keeps theta^2 finite; |t| ~ 1/(2|theta|) ~ 0 there
-    const double q1 = fma(theta, theta, 1.0);
-    const double sq = q1 * rsqrt(q1);              // sqrt(theta^2 + 1)
-    double t = 1.0 / (fabs(theta) + sq);
-    t = nz ? copysign(t, theta) : 0.0;
-    const double c = rsqrt(fma(t, t, 1.0));
-    const double s = t * c;
-    const double swr = s * er, swi = s * ei;       // s * e,  e = a_pq / |a_pq|
+    double c, swr, swi, t, g;
+    jrot_params(Ar[p][q], Ai[p][q], app, aqq, c, swr, swi, t, g);
 #pragma unroll
     for (int k = 0; k < MA; ++k) {
         if (k == p || k == q) continue;
-        const double kpr = Ar[k][p], kpi = Ai[k][p], kqr = Ar[k][q], kqi = Ai[k][q];
-        const double npr = c * kpr - (swr * kqr + swi * kqi);
-        const double npi = c * kpi - (swr * kqi - swi * kqr);
-        const double nqr = c * kqr + (swr * kpr - swi * kpi);
-        const double nqi = c * kqi + (swr * kpi + swi * kpr);
+        double npr, npi, nqr, nqi;
+        jrot_mix(c, swr, swi, Ar[k][p], Ai[k][p], Ar[k][q], Ai[k][q], npr, npi, nqr, nqi);
         Ar[k][p] = npr; Ai[k][p] = npi; Ar[k][q] = nqr; Ai[k][q] = nqi;
         Ar[p][k] = npr; Ai[p][k] = -npi; Ar[q][k] = nqr; Ai[q][k] = -nqi;
     }
-    Ar[p][p] = app - t * g; Ai[p][p] = 0.0;
-    Ar[q][q] = aqq + t * g; Ai[q][q] = 0.0;
+    Ar[p][p] = fma(-t, g, app); Ai[p][p] = 0.0;
+    Ar[q][q] = fma(t, g, aqq);  Ai[q][q] = 0.0;
     Ar[p][q] = 0.0; Ai[p][q] = 0.0; Ar[q][p] = 0.0; Ai[q][p] = 0.0;
 #pragma unroll
     for (int k = 0; k < MA; ++k) {
-        const double kpr = Vr[k][p], kpi = Vi[k][p], kqr = Vr[k][q], kqi = Vi[k][q];
-        Vr[k][p] = c * kpr - (swr * kqr + swi * kqi);
-        Vi[k][p] = c * kpi - (swr * kqi - swi * kqr);
-        Vr[k][q] = c * kqr + (swr * kpr - swi * kpi);
-        Vi[k][q] = c * kqi + (swr * kpi + swi * kpr);
+        double npr, npi, nqr, nqi;
+        jrot_mix(c, swr, swi, Vr[k][p], Vi[k][p], Vr[k][q], Vi[k][q], npr, npi, nqr, nqi);
+        Vr[k][p] = npr; Vi[k][p] = npi; Vr[k][q] = nqr; Vi[k][q] = nqi;
     }
 }
 
@@ -537,8 +570,10 @@ __device__ __forceinline__ void herm_eig_body(const double *Rw, double *ew, doub
             eig_phase(Vr[0][j], Vi[0][j], pr, pi);
 #pragma unroll
             for (int i = 0; i < MA; ++i) {
-                vw[2 * (rank * MA + i)] = Vr[i][j] * pr - Vi[i][j] * pi;
-                vw[2 * (rank * MA + i) + 1] = (i == 0) ? 0.0 : Vr[i][j] * pi + Vi[i][j] * pr;
+                double re, im;
+                eig_out4(Vr[i][j], Vi[i][j], pr, pi, re, im);
+                vw[2 * (rank * MA + i)] = re;
+                vw[2 * (rank * MA + i) + 1] = (i == 0) ? 0.0 : im;
             }
         }
     } else {
@@ -552,6 +587,126 @@ __device__ __forceinline__ void herm_eig_body(const double *Rw, double *ew, doub
                 vw[2 * (rank * M + i)] = Vr[i][j] * pr - Vi[i][j] * pi;
                 vw[2 * (rank * M + i) + 1] = (i == 0) ? 0.0 : Vr[i][j] * pi + Vi[i][j] * pr;
             }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// M = 4 eigensolver with FOUR LANES PER WINDOW (the fused kernel's eigensolver warp: 8 windows per round).
+// The one-lane solver is a single dependent chain (~34 k cycles per round whatever the contention), and that latency
+// is the tail of the fused kernel; here lane j of a group holds column j of A and of V in XOR-relative slots - slot t
+// is row j ^ t - so that for the parallel-ordering step with pairs {j, j ^ X} every register index is a compile-time
+// constant: own 2x2 block = slots {0, X}, the two rows of the other pair = slots {O, O ^ X}, and row k of the mate's
+// column sits in the mate's slot t ^ X.  Both lanes of a pair compute the pair's rotation from identical inputs.
+// Bit-identical to two sequential jacobi_rotate_bf calls per step (first the pair containing index 0), which
+// tools/emulate_eig4_coop.py checks on the CPU and tests/test_gpu_parity.py (fused == unfused) on the GPU:
+//   phase 1  lanes of the second pair apply the first rotation to their column (a local 2-row mix)
+//   phase 2  exchange the two off-block rows with the mate
+//   phase 3  column mix with the own pair's rotation; own 2x2 block := diag(app - t g, aqq + t g)
+//   phase 4  lanes of the first pair apply the second rotation to their column
+//   V        whole columns mix with the mate's column
+// `live` freezes a window whose sweep test has passed while other windows of the warp go on.
+// ------------------------------------------------------------------------------------------
+template <int X>
+__device__ __forceinline__ void eig4_coop_step(double (&ar)[4], double (&ai)[4], double (&vr)[4], double (&vi)[4], const int j,
+                                               const bool live)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int O = (X == 1) ? 2 : 1, O2 = O ^ X, HB = (X == 1) ? 1 : 2;
+    const bool isq = (j & HB) != 0;           // the larger index of my pair
+    const bool first = (j == 0) || (j == X);  // my pair is the one the sequential order rotates first
+    const double dm = __shfl_xor_sync(FULL, ar[0], X);  // the mate's diagonal element
+    const double app = isq ? dm : ar[0], aqq = isq ? ar[0] : dm;
+    double c, swr, swi, t, g;
+    jrot_params(ar[X], isq ? ai[X] : -ai[X], app, aqq, c, swr, swi, t, g);  // lane p holds conj(a_pq)
+    const double c2 = __shfl_xor_sync(FULL, c, O), swr2 = __shfl_xor_sync(FULL, swr, O), swi2 = __shfl_xor_sync(FULL, swi, O);
+    const bool o_is_p = ((j ^ O) & HB) == 0;  // which of my two off-block rows is the smaller index of the other pair
+    auto other_pair = [&](const bool doit) {
+        const double pr = o_is_p ? ar[O] : ar[O2], pi = o_is_p ? ai[O] : ai[O2];
+        const double qr = o_is_p ? ar[O2] : ar[O], qi = o_is_p ? ai[O2] : ai[O];
+        double npr, npi, nqr, nqi;
+        jrot_mix(c2, swr2, swi2, pr, -pi, qr, -qi, npr, npi, nqr, nqi);  // my column holds the conjugates of rows p, q
+        if (doit) {
+            ar[O] = o_is_p ? npr : nqr;   ai[O] = o_is_p ? -npi : -nqi;
+            ar[O2] = o_is_p ? nqr : npr;  ai[O2] = o_is_p ? -nqi : -npi;
+        }
+    };
+    other_pair(live && !first);
+    {
+        const double mOr = __shfl_xor_sync(FULL, ar[O2], X), mOi = __shfl_xor_sync(FULL, ai[O2], X);   // mate's entry of my row (slot O)
+        const double mO2r = __shfl_xor_sync(FULL, ar[O], X), mO2i = __shfl_xor_sync(FULL, ai[O], X);   // ... of my row (slot O2)
+        double r0, i0, r1, i1;
+        jrot_mix_half(c, swr, swi, isq, ar[O], ai[O], mOr, mOi, r0, i0);
+        jrot_mix_half(c, swr, swi, isq, ar[O2], ai[O2], mO2r, mO2i, r1, i1);
+        if (live) {
+            ar[O] = r0; ai[O] = i0; ar[O2] = r1; ai[O2] = i1;
+            ar[0] = isq ? fma(t, g, aqq) : fma(-t, g, app);
+            ai[0] = 0.0; ar[X] = 0.0; ai[X] = 0.0;
+        }
+    }
+    other_pair(live && first);
+    double nr[4], ni[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const double mr = __shfl_xor_sync(FULL, vr[s ^ X], X), mi = __shfl_xor_sync(FULL, vi[s ^ X], X);
+        jrot_mix_half(c, swr, swi, isq, vr[s], vi[s], mr, mi, nr[s], ni[s]);
+    }
+    if (live) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { vr[s] = nr[s]; vi[s] = ni[s]; }
+    }
+}
+
+// All 32 lanes must call this together; lane group g = lane >> 2 works on one window (active = group has one),
+// j = lane & 3.  Rw: 4 x 4 complex, row-major interleaved (shared memory); vw: Vt[rank][i] like herm_eig_body.
+__device__ __forceinline__ void herm_eig4_coop(const double *Rw, double *vw, const bool active, const int j)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    double ar[4], ai[4], vr[4], vi[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int row = j ^ s;
+        ar[s] = active ? Rw[2 * (row * 4 + j)] : 0.0;
+        ai[s] = active ? Rw[2 * (row * 4 + j) + 1] : 0.0;
+        vr[s] = (s == 0) ? 1.0 : 0.0;
+        vi[s] = 0.0;
+    }
+    bool live = active;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+#pragma unroll
+        for (int s = 1; s < 4; ++s) off += ar[s] * ar[s] + ai[s] * ai[s];
+        double fro = off + (ar[0] * ar[0] + ai[0] * ai[0]);
+        off += __shfl_xor_sync(FULL, off, 1);
+        fro += __shfl_xor_sync(FULL, fro, 1);
+        off += __shfl_xor_sync(FULL, off, 2);
+        fro += __shfl_xor_sync(FULL, fro, 2);
+        if (off <= 1e-32 * fro || off == 0.0) live = false;  // same test as herm_eig_body (NaN never passes)
+        if (!__any_sync(FULL, live)) break;
+        eig4_coop_step<1>(ar, ai, vr, vi, j, live);
+        eig4_coop_step<2>(ar, ai, vr, vi, j, live);
+        eig4_coop_step<3>(ar, ai, vr, vi, j, live);
+    }
+    // ascending, stable ranks from the four diagonals; phase from component 0 = slot j
+    const double wj = ar[0];
+    int rank = 0;
+#pragma unroll
+    for (int s = 1; s < 4; ++s) {
+        const double wl = __shfl_xor_sync(FULL, wj, s);
+        rank += eig_before(wl, j ^ s, wj, j);
+    }
+    const double v0r = j == 0 ? vr[0] : j == 1 ? vr[1] : j == 2 ? vr[2] : vr[3];
+    const double v0i = j == 0 ? vi[0] : j == 1 ? vi[1] : j == 2 ? vi[2] : vi[3];
+    double pr, pi;
+    eig_phase(v0r, v0i, pr, pi);
+    if (active) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int i = j ^ s;
+            double re, im;
+            eig_out4(vr[s], vi[s], pr, pi, re, im);
+            vw[2 * (rank * 4 + i)] = re;
+            vw[2 * (rank * 4 + i) + 1] = (i == 0) ? 0.0 : im;
         }
     }
 }

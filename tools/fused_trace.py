@@ -26,12 +26,12 @@ for _ in range(3):
 torch.cuda.synchronize()
 tr = np.zeros((148, 16), np.int64)
 blk._lib.music_b200_debug_fused_trace(blk._h, tr.ctypes.data, 148)
-cov_end = tr[:, :2].max(axis=1)
+cov_end = tr[:, 0]
 print("cycles (mean over CTAs):")
-print("  last cov warp done   %9.0f   (first cov warp done %9.0f)" % (cov_end.mean(), tr[:, :2].min(axis=1).mean()))
+print("  last cov warp done   %9.0f   (first cov warp done %9.0f)" % (cov_end.mean(), tr[:, 1].mean()))
 print("  eig warp exit        %9.0f   busy %9.0f in %5.1f rounds -> %7.0f cyc/round" % (tr[:, 8].mean(), tr[:, 9].mean(), tr[:, 10].mean(), (tr[:, 9] / np.maximum(tr[:, 10], 1)).mean()))
 print("  scan warps exit      %9.0f   busy %9.0f in %5.1f passes -> %7.0f cyc/pass" % (tr[:, 11].mean(), tr[:, 12].mean(), tr[:, 13].mean(), (tr[:, 12] / np.maximum(tr[:, 13], 1)).mean()))
 print("  scan: exact-evaluation phase %9.0f cycles, candidates/CTA %7.1f, full-fp64 fallbacks/CTA %5.2f" % (tr[:, 14].mean(), tr[:, 7].mean(), tr[:, 15].mean()))
 print("  scan thread 0 inside the sweeps: issue+slot-wait %9.0f, tile-arrival wait %9.0f, loads+MMA+post %9.0f" % (tr[:, 4].mean(), tr[:, 5].mean(), tr[:, 6].mean()))
 print("  CTA lifetime by %%globaltimer: %.1f us mean -> SM clock %.0f MHz; CTA start skew %.1f us; first start to last end %.1f us" % (tr[:, 3].mean() / 1e3, (tr[:, 11] / (tr[:, 3] / 1e3)).mean(), (tr[:, 2].max() - tr[:, 2].min()) / 1e3, ((tr[:, 2] + tr[:, 3]).max() - tr[:, 2].min()) / 1e3))
-print("  tail after last cov  %9.0f" % (tr[:, 11] - cov_end).mean())
+print("  tail after last cov  %9.0f   (eig warp exit - last cov %9.0f, scan exit - eig exit %9.0f)" % ((tr[:, 11] - cov_end).mean(), (tr[:, 8] - cov_end).mean(), (tr[:, 11] - tr[:, 8]).mean()))
