@@ -35,5 +35,6 @@ d=json.load(open('$OUT/bench_c$c.json')); print('config $c', '%.3e'%d['value'], 
 echo "== ncu full (TMA-tiled covariance, M = 8 and M = 16)"
 for c in 4 5; do timeout 600 ncu --set full --clock-control none --import-source on -k regex:covN -s 3 -c 1 -f -o $OUT/prof_covn_c$c python bench.py --config $c --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-next-rows > $OUT/ncu_covn_c$c.log 2>&1; echo "ncu covN c$c rc=$?"; done
 fi
+echo "== fused-kernel clock64 trace"; timeout 300 python tools/fused_trace.py 2>&1 | grep -v "MUSIC DOA" > $OUT/fused_trace.txt; cat $OUT/fused_trace.txt
 if [ -x tools/microbench ]; then (cd tools && timeout 300 ./microbench) > $OUT/microbench.log 2>&1; head -8 $OUT/microbench.log; fi
 ls -la $OUT

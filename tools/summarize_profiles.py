@@ -95,7 +95,7 @@ for f, name in (("bench_c3.json", "%s_bench_config3.json" % rnd), ("bench_c4.jso
                 ("bench_c5.json", "%s_bench_config5.json" % rnd), ("launches.csv", "%s_launches.csv" % rnd), ("microbench.log", "%s_microbench.txt" % rnd),
                 ("bench.json", "%s_bench_1gpu.json" % rnd), ("bench_ref.json", "%s_bench_reference_arm.json" % rnd),
                 ("bench_MUSIC_B200_FUSED_0.json", "%s_bench_unfused.json" % rnd), ("pytest_gpu.log", "%s_pytest_gpu.txt" % rnd),
-                ("gpu.txt", "%s_gpu.txt" % rnd)):
+                ("gpu.txt", "%s_gpu.txt" % rnd), ("fused_trace.txt", "%s_fused_trace.txt" % rnd)):
     if os.path.exists(os.path.join(src, f)):
         shutil.copy(os.path.join(src, f), os.path.join(dst, name))
 if t1:
