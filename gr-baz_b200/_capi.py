@@ -47,6 +47,14 @@ def load():
         L.music_b200_process_planar_host.restype = ctypes.c_int
         L.music_b200_process_planar_device.argtypes = [vp, fp, u32, u32, fp, fp, fp, fp, vp]
         L.music_b200_process_planar_device.restype = ctypes.c_int
+        L.music_b200_reduce_angles_device.argtypes = [vp, fp, fp, u32, ctypes.c_int, fp, fp, fp, vp]
+        L.music_b200_reduce_angles_device.restype = ctypes.c_int
+        L.music_b200_reduce_spectrum_device.argtypes = [vp, fp, u32, fp, vp]
+        L.music_b200_reduce_spectrum_device.restype = ctypes.c_int
+        L.music_b200_reduce_angles_host.argtypes = [vp, fp, fp, u32, ctypes.c_int, fp, fp, fp]
+        L.music_b200_reduce_angles_host.restype = ctypes.c_int
+        L.music_b200_reduce_spectrum_host.argtypes = [vp, fp, u32, fp]
+        L.music_b200_reduce_spectrum_host.restype = ctypes.c_int
         L.music_b200_set_peak_mode.argtypes = [vp, ctypes.c_int, u32]
         L.music_b200_set_peak_mode.restype = ctypes.c_int
         L.music_b200_set_geometry.argtypes = [vp, fp, ctypes.c_double, ctypes.POINTER(u32)]
@@ -78,7 +86,8 @@ def load():
 
 
 EXPORTS = [
-    "music_b200_version", "music_b200_create", "music_b200_set_table", "music_b200_set_geometry", "music_b200_set_peak_mode",
+    "music_b200_version", "music_b200_create", "music_b200_set_table", "music_b200_set_geometry", "music_b200_set_peak_mode", "music_b200_reduce_angles_device",
+    "music_b200_reduce_spectrum_device", "music_b200_reduce_angles_host", "music_b200_reduce_spectrum_host",
     "music_b200_get_table", "music_b200_steer_entry_host", "music_b200_process_host",
     "music_b200_process_device", "music_b200_process_device_ex", "music_b200_process_planar_host",
     "music_b200_process_planar_device", "music_b200_launch_count",

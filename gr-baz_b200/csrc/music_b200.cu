@@ -24,6 +24,7 @@
 #include "music_covn.cuh"
 #include "music_steer.cuh"
 #include "music_planar.cuh"
+#include "music_reduce.cuh"
 
 using namespace music;
 
@@ -803,6 +804,97 @@ int music_b200_process_planar_host(music_b200 *h, const float *const *streams, u
     flush_host_slot(h, 0, angles, levels, bins);
     flush_host_slot(h, 1, angles, levels, bins);
     return MUSIC_B200_OK;
+}
+
+int music_b200_reduce_angles_device(music_b200 *h, const float *d_angles, const float *d_levels, uint32_t nwindows, int weighted,
+                                    float *d_mean_deg, float *d_resultant, float *d_weight_sum, void *stream)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (!d_angles || !d_mean_deg) return fail(h, MUSIC_B200_EINVAL, "d_angles and d_mean_deg must not be NULL");
+    if (weighted && !d_levels) return fail(h, MUSIC_B200_EINVAL, "level weighting needs d_levels");
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    reduce_angles_kernel<<<h->n, REDUCE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(d_angles, d_levels, (int)nwindows, (int)h->n,
+                                                                                      weighted ? 1 : 0, d_mean_deg, d_resultant, d_weight_sum);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return MUSIC_B200_OK;
+}
+
+int music_b200_reduce_spectrum_device(music_b200 *h, const float *d_spectrum, uint32_t nwindows, float *d_mean, void *stream)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (!d_spectrum || !d_mean) return fail(h, MUSIC_B200_EINVAL, "d_spectrum and d_mean must not be NULL");
+    if (nwindows == 0) return fail(h, MUSIC_B200_EINVAL, "nwindows must be >= 1");
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    reduce_spectrum_kernel<<<(h->K + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_spectrum, (int)nwindows, (int)h->K, d_mean);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return MUSIC_B200_OK;
+}
+
+// host-buffer conveniences: upload, reduce, download (GUI-rate calls; not a throughput path)
+int music_b200_reduce_angles_host(music_b200 *h, const float *angles, const float *levels, uint32_t nwindows, int weighted,
+                                  float *mean_deg, float *resultant, float *weight_sum)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (!angles || !mean_deg) return fail(h, MUSIC_B200_EINVAL, "angles and mean_deg must not be NULL");
+    if (weighted && !levels) return fail(h, MUSIC_B200_EINVAL, "level weighting needs levels");
+    float *d_a = nullptr, *d_l = nullptr, *d_o = nullptr;
+    const size_t nb = (size_t)nwindows * h->n * sizeof(float);
+    int rc = MUSIC_B200_OK;
+    {
+        std::lock_guard<std::mutex> g(h->mutex);
+        CU(h, cudaSetDevice(h->device));
+        if (cudaMalloc(&d_a, std::max<size_t>(nb, 4)) != cudaSuccess || cudaMalloc(&d_o, 3 * h->n * sizeof(float)) != cudaSuccess ||
+            (levels && cudaMalloc(&d_l, std::max<size_t>(nb, 4)) != cudaSuccess)) {
+            cudaFree(d_a); cudaFree(d_o); cudaFree(d_l);
+            return fail(h, MUSIC_B200_ENOMEM, "cudaMalloc failed for the reducer buffers");
+        }
+        cudaMemcpy(d_a, angles, nb, cudaMemcpyHostToDevice);
+        if (levels) cudaMemcpy(d_l, levels, nb, cudaMemcpyHostToDevice);
+    }
+    rc = music_b200_reduce_angles_device(h, d_a, d_l, nwindows, weighted, d_o, d_o + h->n, d_o + 2 * h->n, nullptr);
+    if (rc == MUSIC_B200_OK) {
+        std::vector<float> out(3 * h->n);
+        const cudaError_t e = cudaMemcpy(out.data(), d_o, out.size() * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(h, MUSIC_B200_ECUDA, "reducer failed: %s", cudaGetErrorString(e));
+        else {
+            for (uint32_t i = 0; i < h->n; ++i) {
+                mean_deg[i] = out[i];
+                if (resultant) resultant[i] = out[h->n + i];
+                if (weight_sum) weight_sum[i] = out[2 * h->n + i];
+            }
+        }
+    }
+    cudaFree(d_a); cudaFree(d_o); cudaFree(d_l);
+    return rc;
+}
+
+int music_b200_reduce_spectrum_host(music_b200 *h, const float *spectrum, uint32_t nwindows, float *mean)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (!spectrum || !mean) return fail(h, MUSIC_B200_EINVAL, "spectrum and mean must not be NULL");
+    if (nwindows == 0) return fail(h, MUSIC_B200_EINVAL, "nwindows must be >= 1");
+    float *d_s = nullptr, *d_m = nullptr;
+    const size_t nb = (size_t)nwindows * h->K * sizeof(float);
+    {
+        std::lock_guard<std::mutex> g(h->mutex);
+        CU(h, cudaSetDevice(h->device));
+        if (cudaMalloc(&d_s, nb) != cudaSuccess || cudaMalloc(&d_m, h->K * sizeof(float)) != cudaSuccess) {
+            cudaFree(d_s); cudaFree(d_m);
+            return fail(h, MUSIC_B200_ENOMEM, "cudaMalloc failed for the reducer buffers");
+        }
+        cudaMemcpy(d_s, spectrum, nb, cudaMemcpyHostToDevice);
+    }
+    int rc = music_b200_reduce_spectrum_device(h, d_s, nwindows, d_m, nullptr);
+    if (rc == MUSIC_B200_OK) {
+        const cudaError_t e = cudaMemcpy(mean, d_m, h->K * sizeof(float), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(h, MUSIC_B200_ECUDA, "reducer failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_s); cudaFree(d_m);
+    return rc;
 }
 
 int music_b200_set_peak_mode(music_b200 *h, int mode, uint32_t exclusion_bins)

@@ -100,6 +100,31 @@ class music_doa(object):
             raise ValueError("mode must be one of %s" % sorted(modes))
         _capi.check(self._lib.music_b200_set_peak_mode(self._h, modes[mode], int(exclusion_bins)), self._h)
 
+    # -- extension: GUI-rate reducers -----------------------------
+    def reduce_angles(self, angles, levels=None, weighted=False):
+        """Circular mean (degrees), mean resultant length and total weight per angle slot over the
+        windows of ``angles`` (W, n) float32 - what a compass-type sink
+        (/root/reference/python/doa_compass_control.py:102-108) consumes.  ``levels`` (W, n) marks
+        unfilled slots (level 0) and, with ``weighted``, weights the windows."""
+        a = np.ascontiguousarray(angles, dtype=np.float32).reshape(-1, self.n)
+        l = None if levels is None else np.ascontiguousarray(levels, dtype=np.float32).reshape(-1, self.n)
+        if l is not None and l.shape != a.shape:
+            raise ValueError("levels must have the shape of angles")
+        mean = np.empty(self.n, np.float32)
+        res = np.empty(self.n, np.float32)
+        wsum = np.empty(self.n, np.float32)
+        rc = self._lib.music_b200_reduce_angles_host(self._h, a.ctypes.data, None if l is None else l.ctypes.data, a.shape[0],
+                                                     1 if weighted else 0, mean.ctypes.data, res.ctypes.data, wsum.ctypes.data)
+        _capi.check(rc, self._h)
+        return mean, res, wsum
+
+    def reduce_spectrum(self, spectrum):
+        """Mean pseudospectrum over the windows of ``spectrum`` (W, resolution) float32."""
+        sp = np.ascontiguousarray(spectrum, dtype=np.float32).reshape(-1, self.resolution)
+        mean = np.empty(self.resolution, np.float32)
+        _capi.check(self._lib.music_b200_reduce_spectrum_host(self._h, sp.ctypes.data, sp.shape[0], mean.ctypes.data), self._h)
+        return mean
+
     def array_response_c64(self):
         """The table in use, as complex64 (resolution, m) - what the block holds after the SWIG
         conversion (swig/baz_swig.i:564)."""

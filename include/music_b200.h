@@ -75,6 +75,24 @@ int music_b200_set_table(music_b200 *h, const float *table_c64);
 int music_b200_set_peak_mode(music_b200 *h, int mode, uint32_t exclusion_bins);
 
 /*
+ * Downstream reducers (extension, no reference counterpart): what a GUI-rate consumer such as the DOA
+ * compass (/root/reference/python/doa_compass_control.py:102-108) or a plot sink
+ * (/root/reference/python/plot_sink.py:38) needs from millions of windows per second.
+ *   reduce_angles: for every angle slot i < n the CIRCULAR mean over nwindows of angles[w][i] (degrees in
+ *     [0, 360)), the mean resultant length (1: all windows agree, 0: spread uniformly) and the total
+ *     weight.  A window counts iff levels == NULL or levels[w][i] > 0 (unfilled slots carry level 0);
+ *     weighted != 0 weights each window by its level.  resultant / weight_sum may be NULL.
+ *   reduce_spectrum: mean over nwindows of spectrum[w][k], k < resolution.
+ * _device: buffers in device memory, enqueued on `stream`; _host: host buffers (upload, reduce, download).
+ */
+int music_b200_reduce_angles_device(music_b200 *h, const float *d_angles, const float *d_levels, uint32_t nwindows, int weighted,
+                                    float *d_mean_deg, float *d_resultant, float *d_weight_sum, void *stream);
+int music_b200_reduce_spectrum_device(music_b200 *h, const float *d_spectrum, uint32_t nwindows, float *d_mean, void *stream);
+int music_b200_reduce_angles_host(music_b200 *h, const float *angles, const float *levels, uint32_t nwindows, int weighted,
+                                  float *mean_deg, float *resultant, float *weight_sum);
+int music_b200_reduce_spectrum_host(music_b200 *h, const float *spectrum, uint32_t nwindows, float *mean);
+
+/*
  * Planar input: one c64 stream per antenna instead of interleaved items.  Window w is
  *     x_w(r, c) = streams[r][w * hop + c],   r < m, c < N = nsamples / m,
  * i.e. what the flowgraph in front of the reference block builds on the CPU by interleaving the

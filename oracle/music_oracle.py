@@ -144,6 +144,33 @@ def pick_local_maxima(P, n, resolution, exclusion=0):
     return out
 
 
+def reduce_angles(angles, levels=None, weighted=False):
+    """NOT in the reference: per angle slot, the circular mean over the windows
+    (degrees in [0, 360)), the mean resultant length and the total weight.  A window counts iff levels is None or
+    its level is > 0; weighted = weight by level.  Returns float32 arrays (mean_deg[n], resultant[n], weight[n])."""
+    a = np.asarray(angles, dtype=np.float32).astype(np.float64)
+    W, n = a.shape
+    lv = np.ones((W, n)) if levels is None else np.asarray(levels, dtype=np.float32).astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        valid = lv > 0.0
+    wt = np.where(valid, lv if weighted else 1.0, 0.0)
+    rad = a * (np.pi / 180.0)
+    S = np.sum(wt * np.sin(rad), axis=0)
+    C = np.sum(wt * np.cos(rad), axis=0)
+    Wt = np.sum(wt, axis=0)
+    deg = np.degrees(np.arctan2(S, C))
+    deg = np.where(deg < 0.0, deg + 360.0, deg)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r = np.where(Wt > 0.0, np.sqrt(S * S + C * C) / Wt, 0.0)
+    deg = np.where(Wt > 0.0, deg, 0.0)
+    return deg.astype(np.float32), r.astype(np.float32), Wt.astype(np.float32)
+
+
+def reduce_spectrum(spectrum):
+    """NOT in the reference: mean over the windows of the float32 spectra, accumulated in fp64."""
+    return np.mean(np.asarray(spectrum, dtype=np.float32).astype(np.float64), axis=0).astype(np.float32)
+
+
 def work(in_c64, m, n, table_c64, want_spectrum=True, literal_pick=False, return_internals=False):
     """One window through lib/baz_music_doa.cc:72-161.
 
