@@ -15,6 +15,10 @@ system LAPACK (``eig_sym`` -> zheev/zheevd).  This restatement therefore follows
 reference *source text* line by line and uses numpy's LAPACK ``zheevd`` binding
 (``numpy.linalg.eigh``) - the same routine family Armadillo dispatches to - for the
 eigendecomposition.  Our own golden vectors (``tests/golden``) are produced by this file.
+What narrows the gap: ``oracle/_ref`` compiles the reference's own ``lib/baz_music_doa.cc``
+unmodified against stand-in GNU Radio / Armadillo headers (``oracle/Makefile`` target
+``ref``) and ``tests/test_ref_shim.py`` checks this file against it - the reference's control
+flow is exercised as written, Armadillo's own arithmetic is not.
 
 Reference lines restated (all under /root/reference):
   lib/baz_music_doa.cc:72-161   work()
