@@ -211,6 +211,32 @@ def run_reference(args):
         dt = time.perf_counter() - t
     value = S * args.steps / dt
     sample = "%d windows/step of the config-%d stream (first %d of %d), %d host threads, C port -O3" % (S, args.config, S, W, threads)
+    # For information, next to the timed port: the reference's own work() source where oracle/_ref was prebuilt (it
+    # runs behind a stand-in Armadillo header, so it is NOT the reference's real speed - DESIGN.md section 2 - and not
+    # the line's value; the port above is the faster, hence conservative, baseline).
+    ref_src = None
+    try:
+        from oracle import ref_build
+
+        if ref_build.available():
+            os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")  # one BLAS thread per window-parallel host thread
+            ref_build.lib()
+            S2 = min(S, threads * 2)
+            parts2 = np.array_split(np.arange(S2), min(threads, S2))
+
+            def job2(idx):
+                return ref_build.work_batch(x[idx[0]:idx[-1] + 1], m, n, table, want_spectrum=False)["angles"]
+
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(job2, parts2))
+                t2 = time.perf_counter()
+                list(ex.map(job2, parts2))
+                dt2 = time.perf_counter() - t2
+            ref_src = {"value": S2 / dt2, "unit": "windows/s", "cores": threads, "windows": S2,
+                       "what": "reference lib/baz_music_doa.cc compiled unmodified against stand-in GNU Radio/Armadillo headers "
+                               "(LAPACK zheevd / BLAS zgemm from scipy's OpenBLAS); informational"}
+    except Exception as e:  # informational leg: never let it take the reference arm down
+        ref_src = {"unavailable": str(e)[:200]}
     line = {
         "impl": "reference", "metric": metric_name(cfg), "value": value, "unit": "windows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -218,7 +244,7 @@ def run_reference(args):
         "config": {"workload": workload_name(cfg, args.config, W), "sample_windows_per_step": S},
         "cpu_baseline": {"value": value, "unit": "windows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "reference_source": ref_src,
     }
     print(json.dumps(line))
     return 0
