@@ -4,8 +4,9 @@
 //
 //   warps 0..7   covariance (FP64 pipe): per-warp TMA ring exactly as cov4_tma_kernel; a finished
 //                window's R is pushed into a 64-slot shared-memory queue (in-order publish).
-//   warp  8      eigensolver: one lane per queued window (up to 32 at once), cyclic Jacobi
-//                (herm_eig_body<4>), eigenvectors written next to the queue slot.
+//   warp  8      eigensolver: four lanes per queued window (8 windows per round, herm_eig4_coop in
+//                music_kernels.cuh; bit-identical to the one-lane herm_eig_body<4>, which
+//                MUSIC_B200_EIG4=lane selects), eigenvectors written next to the queue slot.
 //   warps 9..15  pseudospectrum scan + peak pick, up to 8 windows per pass (two sweeps of the table):
 //                  1. SCREEN on the tensor cores: c_k = e_s^H a_k for all bins k and the 4 windows as a
 //                     [bins x 8] x [8 x 8] product in 3xTF32 (mma.sync m16n8k8, hi/lo split of both
@@ -28,7 +29,8 @@
 // significands); the dropped lo*lo term is <= 2^-21|a||e|.  Allowing every one of the <= 24 fp32
 // accumulations a full 2^-23 (truncating adder), |c~ - c| <= (2^-18.4 + 2^-19.2) sum|a_i||e_i| <= 2^-17.8||a||,
 // hence ||c~|^2 - |c|^2| <= 2^-16.8||a||^2, plus 2^-22 for the fp32 squares and the subtraction from
-// fl32(||a||^2).  FZ_B = 2^-15 leaves > 3x margin over this (already pessimistic) bound.
+// fl32(||a||^2).  FZ_B = 2^-15 leaves > 3x margin over this (already pessimistic) bound; a CPU emulation of the
+// screen with truncating fp32 accumulation measures <= 5e-7 ||a||^2, 60x below FZ_B (tests/test_screen_bound.py).
 //
 // Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does per
 // window except the optional spectrum port).
