@@ -54,6 +54,7 @@ struct music_b200 {
     int device = 0;
     int sm_count = 0;
     std::mutex mutex;        // serialises process_*() and set_table(), like d_mutex (:67, :101)
+    std::mutex err_mutex;    // guards `error` alone: fail() may run before `mutex` is taken (argument checks)
     std::string error;
     std::atomic<uint64_t> launches{0};
 
@@ -112,6 +113,7 @@ int fail(music_b200 *h, int code, const char *fmt, ...)
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     if (h) {
+        std::lock_guard<std::mutex> g(h->err_mutex);
         h->error = buf;
     } else {
         std::lock_guard<std::mutex> g(g_err_mutex);
@@ -220,6 +222,18 @@ EncodeTiledFn encode_tiled_fn()
     }();
     return fn;
 }
+
+// Inside the chunk loops of the host entry points an error must not skip the common tail (stream syncs, slot
+// reset): record it in rc and leave the loop instead of returning.
+#define CU_BREAK(h, rc, expr)                                                                    \
+    {                                                                                            \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            rc = fail((h), e_ == cudaErrorMemoryAllocation ? MUSIC_B200_ENOMEM : MUSIC_B200_ECUDA, \
+                      "%s failed: %s", #expr, cudaGetErrorString(e_));                           \
+            break;                                                                               \
+        }                                                                                        \
+    }
 
 constexpr int NSLOT = 3;           // workspace ring for the cov -> eig/scan software pipeline
 constexpr uint32_t MIN_SUB = 1024; // windows; below 2*MIN_SUB a call is not split
@@ -578,9 +592,14 @@ int music_b200_version(void) { return 1; }
 
 const char *music_b200_last_error(const music_b200 *h)
 {
-    if (h) return h->error.c_str();
+    static thread_local std::string copy;  // the returned text stays valid until this thread's next call
+    if (h) {
+        music_b200 *hm = const_cast<music_b200 *>(h);
+        std::lock_guard<std::mutex> g(hm->err_mutex);
+        copy = hm->error;
+        return copy.c_str();
+    }
     std::lock_guard<std::mutex> g(g_err_mutex);
-    static thread_local std::string copy;
     copy = g_create_error;
     return copy.c_str();
 }
@@ -703,7 +722,7 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
     };
     rc = init();
     if (rc != MUSIC_B200_OK) {
-        fail(nullptr, rc, "%s", h->error.c_str());
+        fail(nullptr, rc, "%s", std::string(h->error).c_str());
         music_b200_destroy(h);
         return rc;
     }
@@ -762,8 +781,9 @@ int music_b200_process_planar_host(music_b200 *h, const float *const *streams, u
     CU(h, cudaSetDevice(h->device));
     // staging holds cap * m * N samples; a chunk of C windows needs m * ((C - 1) * hop + N) of them, laid out planar
     const size_t N = h->N;
-    size_t cap = std::max<size_t>(SCAN_B, ((size_t)32 << 20) / ((size_t)h->nsamples * 8));
+    size_t cap = std::max<size_t>(SCAN_B, ((size_t)32 << 20) / std::max((size_t)h->nsamples * 8, spectrum ? (size_t)h->K * sizeof(float) : (size_t)0));
     cap = std::max<size_t>(cap, ((size_t)hop + N - 1) / N + 1);  // at least one window when hop > N
+    h->slot_W[0] = h->slot_W[1] = 0;  // nothing pending from an earlier (possibly failed) call
     int rc = ensure_host_staging(h, (uint32_t)cap, spectrum != nullptr);
     if (rc) return rc;
     cap = h->host_chunk;
@@ -777,23 +797,24 @@ int music_b200_process_planar_host(music_b200 *h, const float *const *streams, u
         const uint32_t W = std::min(chunk, nwindows - w0);
         cudaStream_t st = h->streams[s];
         if (it >= 2) {
-            CU(h, cudaStreamSynchronize(st));
+            CU_BREAK(h, rc, cudaStreamSynchronize(st));
             flush_host_slot(h, s, angles, levels, bins);
         }
         const size_t seg = (size_t)(W - 1) * hop + N;  // snapshots of each stream this chunk touches
         PlanarStreams S;
         for (uint32_t r = 0; r < MAXM; ++r) S.p[r] = nullptr;
-        for (uint32_t r = 0; r < h->m; ++r) {
+        for (uint32_t r = 0; r < h->m && rc == MUSIC_B200_OK; ++r) {
             float *dst = h->d_in[s] + (size_t)r * seg * 2;
-            CU(h, cudaMemcpyAsync(dst, streams[r] + ((size_t)w0 * hop) * 2, seg * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+            CU_BREAK(h, rc, cudaMemcpyAsync(dst, streams[r] + ((size_t)w0 * hop) * 2, seg * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
             S.p[r] = reinterpret_cast<const float2 *>(dst);
         }
+        if (rc) break;
         rc = enqueue_device(h, nullptr, W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
                             nullptr, nullptr, nullptr, st, s, false, &S, hop);
         if (rc) break;
         rc = download_host_slot(h, s, w0, W, levels != nullptr, bins != nullptr, st);
         if (rc) break;
-        if (spectrum) CU(h, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (spectrum) CU_BREAK(h, rc, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
     cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
@@ -970,9 +991,13 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
     CU(h, cudaSetDevice(h->device));
     // chunk: ~32 MiB of input per copy, so that H2D of chunk i+1 overlaps compute of chunk i
     const size_t win_bytes = (size_t)h->nsamples * 2 * sizeof(float);
-    uint32_t chunk = (uint32_t)std::max<size_t>(SCAN_B, ((size_t)32 << 20) / win_bytes);
+    // (with the spectrum port connected a window also returns K floats: bound the chunk by the larger of the two, so that
+    // short windows on a fine grid do not blow up the spectrum staging)
+    const size_t per_win = std::max(win_bytes, spectrum ? (size_t)h->K * sizeof(float) : (size_t)0);
+    uint32_t chunk = (uint32_t)std::max<size_t>(SCAN_B, ((size_t)32 << 20) / per_win);
     chunk = std::min(chunk, (nwindows + 1) / 2 > SCAN_B ? (nwindows + 1) / 2 : nwindows);
     chunk = std::max<uint32_t>(1, chunk);
+    h->slot_W[0] = h->slot_W[1] = 0;  // nothing pending from an earlier (possibly failed) call
     int rc = ensure_host_staging(h, chunk, spectrum != nullptr);
     if (rc) return rc;
     // Each of the two copy streams computes in its own workspace slot, so H2D, kernels and D2H of
@@ -984,16 +1009,16 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
         const uint32_t W = std::min(chunk, nwindows - w0);
         cudaStream_t st = h->streams[s];
         if (it >= 2) {
-            CU(h, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
+            CU_BREAK(h, rc, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
             flush_host_slot(h, s, angles, levels, bins);
         }
-        CU(h, cudaMemcpyAsync(h->d_in[s], in_c64 + (size_t)w0 * h->nsamples * 2, (size_t)W * win_bytes, cudaMemcpyHostToDevice, st));
+        CU_BREAK(h, rc, cudaMemcpyAsync(h->d_in[s], in_c64 + (size_t)w0 * h->nsamples * 2, (size_t)W * win_bytes, cudaMemcpyHostToDevice, st));
         rc = enqueue_device(h, h->d_in[s], W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
                             nullptr, nullptr, nullptr, st, s, false);
         if (rc) break;
         rc = download_host_slot(h, s, w0, W, levels != nullptr, bins != nullptr, st);
         if (rc) break;
-        if (spectrum) CU(h, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (spectrum) CU_BREAK(h, rc, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
     cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);

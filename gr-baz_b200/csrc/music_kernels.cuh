@@ -1132,11 +1132,13 @@ __device__ __forceinline__ void scan_bin(const double (&ar)[M], const double (&a
     for (int i = 1; i < M; ++i) {
 #pragma unroll
         for (int b = 0; b < WPT; ++b) {
+            // same association as complement_denominator (the cold path): fma(e.x, a, fma(e.y, a', c)), so that a bin
+            // evaluated hot in one thread and cold in another rounds identically (exact mirror ties stay exact)
             const double2 e = lds_f64x2(ev[b] + sig + 16 * i);
-            cr[b] = fma(e.x, ar[i], cr[b]);
-            ci[b] = fma(e.x, ai[i], ci[b]);
             cr[b] = fma(e.y, ai[i], cr[b]);
             ci[b] = fma(-e.y, ar[i], ci[b]);
+            cr[b] = fma(e.x, ar[i], cr[b]);
+            ci[b] = fma(e.x, ai[i], ci[b]);
         }
     }
     const double gna = COMPLEMENT_GUARD * na;

@@ -101,7 +101,9 @@ int music_b200_reduce_spectrum_host(music_b200 *h, const float *spectrum, uint32
  * baz_music_doa::work() reshapes it back (/root/reference/lib/baz_music_doa.cc:82-84).
  * hop == N: back-to-back windows; hop < N: windows overlap by N - hop snapshots; hop > N: gaps.
  * Each stream must hold (nwindows - 1) * hop + N samples.  Outputs as in process_host/_device.
- * Results are identical to process_*() on the interleaved windows.
+ * Results equal those of process_*() on the interleaved windows up to fp64 rounding of R (the planar kernels sum the
+ * snapshots in a different order for m > 4): P(theta) agrees to ~1e-12 relative, peak bins are equal except where two
+ * bins' strengths tie to within that rounding (in practice the 90/270 degree pair of an x-axis ULA).
  *   _host  : streams[r] are host pointers (copied to the device in chunks, planar, no interleave)
  *   _device: d_streams is a HOST array of m device pointers (8-byte aligned), work is enqueued on `stream`
  */

@@ -29,6 +29,7 @@
 #include <music_b200.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 

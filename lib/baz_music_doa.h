@@ -67,7 +67,6 @@ private:
     unsigned int d_resolution;
     music_b200 *d_handle;
     std::vector<int> d_bins;
-    std::vector<float> d_levels_scratch;
     gr::thread::mutex d_mutex;
 };
 

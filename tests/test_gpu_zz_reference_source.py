@@ -29,6 +29,8 @@ def reference_source():
 @pytest.mark.parametrize("base,over,W", [
     (1, {}, 24), (1, {"n": 2}, 12), (2, {"snapshots": 1024}, 12), (4, {"snapshots": 512}, 10),
     (5, {"snapshots": 512, "resolution": 1800}, 8), (1, {"m": 6, "geometry": "uca", "n": 2}, 8),
+    # the BASELINE shapes at FULL size (configs[1..4]): C2 4x4096x3600, C3 8x8192x7200, C4 8x4096x3600, C5 16x4096x3600 n=2
+    (2, {}, 16), (3, {}, 8), (4, {}, 8), (5, {}, 8),
 ])
 def test_cuda_path_matches_the_reference_source(base, over, W):
     rb = reference_source()
