@@ -41,6 +41,22 @@ def load():
         L.music_b200_version.restype = ctypes.c_int
         L.music_b200_create.argtypes = [ctypes.POINTER(vp), u32, u32, u32, u32, fp, ctypes.c_int]
         L.music_b200_create.restype = ctypes.c_int
+        L.music_b200_create_multi.argtypes = [ctypes.POINTER(vp), u32, u32, u32, u32, fp, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        L.music_b200_create_multi.restype = ctypes.c_int
+        L.music_b200_device_count.argtypes = [vp]
+        L.music_b200_device_count.restype = ctypes.c_int
+        L.music_b200_process_device_sharded.argtypes = [vp, fp, u32, fp, fp, fp, fp]
+        L.music_b200_process_device_sharded.restype = ctypes.c_int
+        L.music_b200_gather_create.argtypes = [vp, u32, fp]
+        L.music_b200_gather_create.restype = ctypes.c_int
+        L.music_b200_gather_attach.argtypes = [vp, ctypes.c_int, ctypes.c_int, fp]
+        L.music_b200_gather_attach.restype = ctypes.c_int
+        L.music_b200_gather_wait.argtypes = [vp, vp]
+        L.music_b200_gather_wait.restype = ctypes.c_int
+        L.music_b200_gather_buffer.argtypes = [vp]
+        L.music_b200_gather_buffer.restype = ctypes.c_void_p
+        L.music_b200_gather_read.argtypes = [vp, fp, u32]
+        L.music_b200_gather_read.restype = ctypes.c_int
         L.music_b200_set_table.argtypes = [vp, fp]
         L.music_b200_set_table.restype = ctypes.c_int
         L.music_b200_process_planar_host.argtypes = [vp, fp, u32, u32, fp, fp, fp, fp]
@@ -77,6 +93,8 @@ def load():
         L.music_b200_get_stage_times.restype = ctypes.c_int
         L.music_b200_debug_fused_trace.argtypes = [vp, ctypes.c_void_p, ctypes.c_int]
         L.music_b200_debug_fused_trace.restype = ctypes.c_int
+        L.music_b200_debug_fused8_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+        L.music_b200_debug_fused8_stats.restype = ctypes.c_int
         L.music_b200_last_error.argtypes = [vp]
         L.music_b200_last_error.restype = ctypes.c_char_p
         L.music_b200_destroy.argtypes = [vp]
@@ -86,12 +104,14 @@ def load():
 
 
 EXPORTS = [
-    "music_b200_version", "music_b200_create", "music_b200_set_table", "music_b200_set_geometry", "music_b200_set_peak_mode", "music_b200_reduce_angles_device",
+    "music_b200_version", "music_b200_create", "music_b200_create_multi", "music_b200_device_count",
+    "music_b200_process_device_sharded", "music_b200_gather_create", "music_b200_gather_attach", "music_b200_gather_wait",
+    "music_b200_gather_buffer", "music_b200_gather_read", "music_b200_set_table", "music_b200_set_geometry", "music_b200_set_peak_mode", "music_b200_reduce_angles_device",
     "music_b200_reduce_spectrum_device", "music_b200_reduce_angles_host", "music_b200_reduce_spectrum_host",
     "music_b200_get_table", "music_b200_steer_entry_host", "music_b200_process_host",
     "music_b200_process_device", "music_b200_process_device_ex", "music_b200_process_planar_host",
     "music_b200_process_planar_device", "music_b200_launch_count",
-    "music_b200_set_stage_timing", "music_b200_get_stage_times", "music_b200_debug_fused_trace",
+    "music_b200_set_stage_timing", "music_b200_get_stage_times", "music_b200_debug_fused_trace", "music_b200_debug_fused8_stats",
     "music_b200_last_error", "music_b200_destroy",
 ]
 

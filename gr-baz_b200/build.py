@@ -13,11 +13,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libmusic_b200.so")
 SOURCES = ["music_b200.cu"]
-DEPS = ["music_b200.cu", "music_kernels.cuh", "music_fused.cuh", "music_covn.cuh", "music_steer.cuh", "music_planar.cuh", "music_reduce.cuh", os.path.join("..", "..", "include", "music_b200.h")]
+DEPS = ["music_b200.cu", "music_kernels.cuh", "music_fused.cuh", "music_eig4p.cuh", "music_covn.cuh", "music_fused8.cuh", "music_steer.cuh", "music_planar.cuh", "music_reduce.cuh", os.path.join("..", "..", "include", "music_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

@@ -7,6 +7,7 @@
 #include "../../include/music_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <atomic>
@@ -22,6 +23,7 @@
 #include "music_kernels.cuh"
 #include "music_fused.cuh"
 #include "music_covn.cuh"
+#include "music_fused8.cuh"
 #include "music_steer.cuh"
 #include "music_planar.cuh"
 #include "music_reduce.cuh"
@@ -75,9 +77,11 @@ struct music_b200 {
     cudaEvent_t ev_in = nullptr;
     bool pipeline = false;   // MUSIC_B200_PIPE=1 enables the sub-batch pipeline (launch-bound at 10k windows: off)
     unsigned *work_ctr = nullptr;      // fused kernel: [0] window tickets, [1] finished CTAs (self-resetting)
-    cudaEvent_t fused_done = nullptr;  // launches of one handle are serialised (they share work_ctr)
-    bool fused_used = false;
-    bool eig_coop = true;             // MUSIC_B200_EIG4=lane selects the one-lane-per-window eigensolver in the fused kernel
+    cudaEvent_t fused_done = nullptr;  // orders persistent launches that share a ticket counter but not a stream
+    bool fused_used[2] = {false, false};
+    int eig_mode = 0;                 // fused kernel: 0 principal eigenvector by squaring (default), 1 / 2 Jacobi with four lanes / one lane per window (MUSIC_B200_EIG=jacobi|jacobi1)
+    unsigned *f8_stats = nullptr;     // fused M = 8 kernel: windows solved by squaring / by the Jacobi fallback
+    int mma_fin_max = 2;              // fused kernel: tensor-core passes start while <= this many covariance warps are done (MUSIC_B200_MMA_FIN; -1: fp64 drain only)
     long long *fused_trace = nullptr;  // MUSIC_B200_TRACE=1: per-CTA clock64 trace of the fused kernel (tools/fused_trace.py)
     bool fused = true;       // MUSIC_B200_FUSED=0 forces the three-kernel path
     bool covn = true;        // MUSIC_B200_COVN=0: M = 8/16 covariance by the v1 LDG tile kernels
@@ -101,6 +105,26 @@ struct music_b200 {
     uint32_t slot_w0[2] = {0, 0}, slot_W[2] = {0, 0};
     uint32_t host_chunk = 0;
     bool host_spec_alloc = false;
+    cudaStream_t last_fused_stream[2] = {nullptr, nullptr};  // per ticket counter: launches on one stream need no event
+
+    // caller memory registered for DMA (cudaHostRegister), newest last: GNU Radio hands work() the same pageable
+    // circular buffers over and over, so a range is pinned once and found again on every later call
+    struct HostReg { uintptr_t base; size_t len; };
+    std::vector<HostReg> hostregs;
+    bool hostreg = true;   // MUSIC_B200_HOSTREG=0: never register (pageable copies go through the driver's staging)
+
+    // multi-device handle (music_b200_create_multi): one child per device, windows dealt w -> child w mod G
+    std::vector<music_b200 *> kids;
+
+    // fused all-gather of the peak bins (music_b200_gather_*): peer-mapped buffers, epoch flags
+    int32_t *gather_buf = nullptr;
+    unsigned *gather_flags = nullptr;
+    size_t gather_cap = 0;
+    int32_t *peer_bins[MAX_PEERS] = {};
+    unsigned *peer_flags[MAX_PEERS] = {};
+    bool peer_ipc[MAX_PEERS] = {};
+    int gather_G = 0, gather_rank = 0;
+    unsigned gather_epoch = 0;
 };
 
 namespace {
@@ -304,8 +328,26 @@ cudaEvent_t *timing_events(music_b200 *h)
     return p;
 }
 
+// Ticket counter pair `slot` (0 / 1) for a persistent kernel about to be launched on `st`.  The counters re-arm
+// themselves at the end of a launch, so launches that share a pair must not overlap: on one stream that is stream
+// order; when the stream changes, the new stream first waits for everything enqueued on the previous one.
+unsigned *ticket_counter(music_b200 *h, int slot, cudaStream_t st)
+{
+    slot &= 1;
+    if (h->fused_used[slot] && h->last_fused_stream[slot] != st) {
+        if (cudaEventRecord(h->fused_done, h->last_fused_stream[slot]) != cudaSuccess ||
+            cudaStreamWaitEvent(st, h->fused_done, 0) != cudaSuccess) {
+            cudaGetLastError();        // e.g. the previous stream no longer exists
+            cudaDeviceSynchronize();
+        }
+    }
+    h->fused_used[slot] = true;
+    h->last_fused_stream[slot] = st;
+    return h->work_ctr + 2 * slot;
+}
+
 // K1: covariance of W windows into ws.R, on `st`.
-void launch_cov(music_b200 *h, const Workspace &ws, const float *d_in, uint32_t W, cudaStream_t st)
+void launch_cov(music_b200 *h, const Workspace &ws, const float *d_in, uint32_t W, cudaStream_t st, int ctr_slot)
 {
     const int M = (int)h->m, N = (int)h->N;
     if (M == 4 && h->cov_tma_stages > 0) {
@@ -332,11 +374,9 @@ void launch_cov(music_b200 *h, const Workspace &ws, const float *d_in, uint32_t 
             constexpr int groups8 = CN_WARPS / CovNJobs<8>::J, groups16 = CN_WARPS / CovNJobs<16>::J;
             const int groups = M == 8 ? groups8 : groups16;
             const int grid = std::min<int>(h->sm_count, (int)((W + groups - 1) / groups));
-            if (h->fused_used) cudaStreamWaitEvent(st, h->fused_done, 0);  // shares work_ctr: serialise launches
-            if (M == 8) covN_tma_kernel<8><<<grid, CN_WARPS * 32, CN_SMEM, st>>>(tm, ws.R, (int)W, N, h->work_ctr);
-            else covN_tma_kernel<16><<<grid, CN_WARPS * 32, CN_SMEM, st>>>(tm, ws.R, (int)W, N, h->work_ctr);
-            cudaEventRecord(h->fused_done, st);
-            h->fused_used = true;
+            unsigned *ctr = ticket_counter(h, ctr_slot, st);
+            if (M == 8) covN_tma_kernel<8><<<grid, CN_WARPS * 32, CN_SMEM, st>>>(tm, ws.R, (int)W, N, ctr);
+            else covN_tma_kernel<16><<<grid, CN_WARPS * 32, CN_SMEM, st>>>(tm, ws.R, (int)W, N, ctr);
             h->launches++;
             return;
         }
@@ -367,10 +407,52 @@ void launch_cov(music_b200 *h, const Workspace &ws, const float *d_in, uint32_t 
     }
 }
 
+// Output descriptor of a batch whose first window is local window w0 of the call: local pointers as given, plus the
+// peers' gather buffers (music_b200_gather_attach / process_device_sharded) advanced to the same stream position.
+PeakOut make_peak_out(const music_b200 *h, float *d_ang, float *d_lvl, int32_t *d_bins, size_t w0)
+{
+    PeakOut po;
+    po.angles = d_ang; po.levels = d_lvl; po.bins = d_bins;
+    po.npeer = h->gather_G; po.rank = h->gather_rank; po.n = (int)h->n;
+    for (int p = 0; p < MAX_PEERS; ++p)
+        po.peer[p] = (p < h->gather_G && h->peer_bins[p]) ? h->peer_bins[p] + w0 * (size_t)h->gather_G * h->n : nullptr;
+    return po;
+}
+
+GatherFlags make_gather_flags(const music_b200 *h, bool signal)
+{
+    GatherFlags gf;
+    for (int p = 0; p < MAX_PEERS; ++p) gf.peer[p] = p < h->gather_G ? h->peer_flags[p] : nullptr;
+    gf.epoch = (signal && h->gather_G > 0 && h->peer_flags[0]) ? h->gather_epoch : 0u;
+    return gf;
+}
+
+// raises this GPU's epoch flag at every peer once everything before it on the stream is done (unfused paths; the
+// fused kernel signals from its last CTA)
+__global__ void gather_signal_kernel(const GatherFlags gf, int npeer, int rank)
+{
+    if ((int)threadIdx.x < npeer) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gf.peer[threadIdx.x] + rank), "r"(gf.epoch) : "memory");
+    }
+}
+
+// consumer side: returns when every peer's flag in THIS GPU's array has reached `epoch`
+__global__ void gather_wait_kernel(const unsigned *flags, int npeer, unsigned epoch)
+{
+    if ((int)threadIdx.x < npeer) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            __nanosleep(200);
+        } while (true);
+    }
+}
+
 // K2 + K3 (+ top-n) of W windows from ws.R, on `st`.  tev (optional) = timing events [1..4].
-int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, float *d_ang, float *d_lvl, float *d_spec,
-                    int32_t *d_bins, double *d_P64_out, double *d_R_out, double *d_ev_out, cudaStream_t st,
-                    cudaEvent_t *tev)
+int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, const PeakOut &po, float *d_spec,
+                    double *d_P64_out, double *d_R_out, double *d_ev_out, cudaStream_t st, cudaEvent_t *tev)
 {
     const int M = (int)h->m;
     const double *soa = h->table[h->cur_table].soa;
@@ -393,7 +475,6 @@ int launch_eig_scan(music_b200 *h, const Workspace &ws, uint32_t W, float *d_ang
     const bool argmax = (h->n == 1) && !local;
     const bool need_p64 = !argmax || d_P64_out != nullptr;
     double *p64 = d_P64_out ? d_P64_out : ws.P64;
-    PeakOut po{d_ang, d_lvl, d_bins};
     const bool fast = argmax && !need_p64 && !d_spec && (M == 4 || M == 8 || M == 16) && h->scan_fast;
     if (fast) {
         const int grid = (W + SCAN_B - 1) / SCAN_B;
@@ -462,22 +543,45 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
         const int grid = std::min<int>(h->sm_count, (int)((nwindows + FZ_COV_WARPS - 1) / FZ_COV_WARPS));
-        if (h->fused_used) CU(h, cudaStreamWaitEvent(st, h->fused_done, 0));
+        unsigned *ctr = ticket_counter(h, first_slot, st);
         const DeviceTable &tb = h->table[h->cur_table];
+        const PeakOut po = make_peak_out(h, d_ang, d_lvl, d_bins, 0);
+        const GatherFlags gf = make_gather_flags(h, true);
         if (planar)
             music4_fused_kernel<true><<<grid, FZ_THREADS, FZ_SMEM, st>>>(nullptr, *planar, 0ull, hop, tb.fz, tb.c64, tb.na_max, (int)nwindows,
-                                                                         (int)h->N, (int)h->K, PeakOut{d_ang, d_lvl, d_bins},
-                                                                         h->work_ctr, h->fused_trace, h->eig_coop ? 1 : 0);
+                                                                         (int)h->N, (int)h->K, po, ctr, h->fused_trace, h->eig_mode,
+                                                                         tb.soa, gf, h->mma_fin_max);
         else
             music4_fused_kernel<false><<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, PlanarStreams{}, 0ull, 0u, tb.fz, tb.c64, tb.na_max,
-                                                                          (int)nwindows, (int)h->N, (int)h->K,
-                                                                          PeakOut{d_ang, d_lvl, d_bins}, h->work_ctr, h->fused_trace, h->eig_coop ? 1 : 0);
+                                                                          (int)nwindows, (int)h->N, (int)h->K, po, ctr, h->fused_trace,
+                                                                          h->eig_mode, tb.soa, gf, h->mma_fin_max);
         h->launches++;
-        CU(h, cudaEventRecord(h->fused_done, st));
-        h->fused_used = true;
         if (tev) for (int i = 1; i < 5; ++i) cudaEventRecord(tev[i], st);
         CU(h, cudaGetLastError());
         return MUSIC_B200_OK;
+    }
+    if (!planar && h->fused && !local_peaks && h->m == 8 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev && h->N >= 128 &&
+        h->N % 2 == 0 && encode_tiled_fn()) {
+        // M = 8: whole call in one persistent launch (music_fused8.cuh); R and the eigenvectors stay in shared memory
+        CUtensorMap tm;
+        const cuuint64_t gdim[3] = {32u, (cuuint64_t)(h->N / 2), (cuuint64_t)nwindows};  // 128-byte rows of two snapshots
+        const cuuint64_t gstr[2] = {128u, (cuuint64_t)64 * (cuuint64_t)h->N};
+        const cuuint32_t box[3] = {32u, (cuuint32_t)(F8_STAGE / 128), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        if (encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(d_in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            cudaEvent_t *tev = timing_events(h);
+            if (tev) cudaEventRecord(tev[0], st);
+            const int grid = std::min<int>(h->sm_count, (int)((nwindows + F8_WARPS - 1) / F8_WARPS));
+            unsigned *ctr = ticket_counter(h, first_slot, st);
+            music8_fused_kernel<<<grid, F8_WARPS * 32, F8_SMEM, st>>>(tm, h->table[h->cur_table].soa, (int)nwindows, (int)h->N, (int)h->K,
+                                                                     make_peak_out(h, d_ang, d_lvl, d_bins, 0), ctr, make_gather_flags(h, true),
+                                                                     h->eig_mode ? 1 : 0, h->f8_stats);
+            h->launches++;
+            if (tev) for (int i = 1; i < 5; ++i) cudaEventRecord(tev[i], st);
+            CU(h, cudaGetLastError());
+            return MUSIC_B200_OK;
+        }
     }
     const bool internal_p64 = (h->n != 1 || local_peaks) && !d_P64;
     const uint32_t max_sub = max_sub_windows(h, internal_p64);
@@ -505,14 +609,16 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], s_cov);
         if (planar) launch_cov_planar(h, ws, *planar, (unsigned long long)w0 * hop, hop, W, s_cov);
-        else launch_cov(h, ws, d_in + (size_t)w0 * h->nsamples * 2, W, s_cov);
+        else launch_cov(h, ws, d_in + (size_t)w0 * h->nsamples * 2, W, s_cov, first_slot);
         if (tev) cudaEventRecord(tev[1], s_cov);
         if (pipe) {
             CU(h, cudaEventRecord(ws.cov_done, s_cov));
             CU(h, cudaStreamWaitEvent(s_scan, ws.cov_done, 0));
         }
-        rc = launch_eig_scan(h, ws, W, d_ang + (size_t)w0 * h->n, d_lvl ? d_lvl + (size_t)w0 * h->n : nullptr,
-                             d_spec ? d_spec + (size_t)w0 * h->K : nullptr, d_bins ? d_bins + (size_t)w0 * h->n : nullptr,
+        rc = launch_eig_scan(h, ws, W,
+                             make_peak_out(h, d_ang + (size_t)w0 * h->n, d_lvl ? d_lvl + (size_t)w0 * h->n : nullptr,
+                                           d_bins ? d_bins + (size_t)w0 * h->n : nullptr, w0),
+                             d_spec ? d_spec + (size_t)w0 * h->K : nullptr,
                              d_P64 ? d_P64 + (size_t)w0 * h->K : nullptr, d_R ? d_R + (size_t)w0 * h->m * h->m * 2 : nullptr,
                              d_ev ? d_ev + (size_t)w0 * h->m : nullptr, s_scan, tev);
         if (rc) return rc;
@@ -522,7 +628,62 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         slot = pipe ? (slot + 1) % NSLOT : slot;
     }
     if (pipe && last_slot >= 0) CU(h, cudaStreamWaitEvent(st, h->ws[last_slot].scan_done, 0));
+    if (h->gather_G > 0) {
+        const GatherFlags gf = make_gather_flags(h, true);
+        if (gf.epoch) {
+            gather_signal_kernel<<<1, 32, 0, st>>>(gf, h->gather_G, h->gather_rank);
+            h->launches++;
+        }
+    }
     return MUSIC_B200_OK;
+}
+
+struct NvtxRange {  // SURVEY.md section 5 tracing hook: ranges show up in nsys / ncu timelines, free when no tool is attached
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+// Makes [ptr, ptr + bytes) DMA-able if it is ordinary pageable memory: page-aligned cudaHostRegister, remembered in
+// the handle (at most 16 ranges, oldest evicted).  Memory that is already pinned (cudaHostAlloc, registered by the
+// caller) or that cannot be registered is left alone - the copies then take the driver's staged path.
+void host_register(music_b200 *h, const void *ptr, size_t bytes, bool read_only)
+{
+    if (!h->hostreg || !ptr || bytes < ((size_t)1 << 20)) return;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(ptr), page = 4096;
+    const uintptr_t lo = a & ~(page - 1), hi = (a + bytes + page - 1) & ~(page - 1);
+    for (size_t i = 0; i < h->hostregs.size(); ++i)
+        if (h->hostregs[i].base <= lo && hi <= h->hostregs[i].base + h->hostregs[i].len) return;  // already ours
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess) {
+        if (at.type != cudaMemoryTypeUnregistered) return;  // pinned by the caller (or not host memory at all)
+    } else {
+        cudaGetLastError();
+    }
+    NvtxRange r("music_b200: cudaHostRegister");
+    // ranges of ours that overlap the new one (a circular buffer seen at a shifted offset): drop them first
+    for (size_t i = 0; i < h->hostregs.size();) {
+        const music_b200::HostReg &g = h->hostregs[i];
+        if (g.base < hi && lo < g.base + g.len) {
+            cudaHostUnregister(reinterpret_cast<void *>(g.base));
+            h->hostregs.erase(h->hostregs.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+    cudaError_t e = cudaHostRegister(reinterpret_cast<void *>(lo), hi - lo, cudaHostRegisterPortable | (read_only ? cudaHostRegisterReadOnly : 0));
+    if (e != cudaSuccess && read_only) {
+        cudaGetLastError();
+        e = cudaHostRegister(reinterpret_cast<void *>(lo), hi - lo, cudaHostRegisterPortable);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // not registrable (e.g. a read-only mapping): pageable copies still work
+        return;
+    }
+    if (h->hostregs.size() >= 16) {
+        cudaHostUnregister(reinterpret_cast<void *>(h->hostregs.front().base));
+        h->hostregs.erase(h->hostregs.begin());
+    }
+    h->hostregs.push_back(music_b200::HostReg{lo, (size_t)(hi - lo)});
 }
 
 void free_host_staging(music_b200 *h)
@@ -560,15 +721,28 @@ int ensure_host_staging(music_b200 *h, uint32_t chunk, bool spec)
     return MUSIC_B200_OK;
 }
 
-// results of the chunk last computed in staging slot s: pinned mirror -> caller memory (the slot's stream is idle)
-void flush_host_slot(music_b200 *h, int s, float *angles, float *levels, int32_t *bins)
+// results of the chunk last computed in staging slot s: pinned mirror -> caller memory (the slot's stream is idle).
+// The chunk holds the windows w = (slot_w0 + i) * G + g of the call (G = 1, g = 0 on a single-device handle).
+void flush_host_slot(music_b200 *h, int s, float *angles, float *levels, int32_t *bins, uint32_t G = 1, uint32_t g = 0)
 {
     const uint32_t W = h->slot_W[s];
     if (!W) return;
-    const size_t off = (size_t)h->slot_w0[s] * h->n, cnt = (size_t)W * h->n;
-    memcpy(angles + off, h->p_ang[s], cnt * sizeof(float));
-    if (levels) memcpy(levels + off, h->p_lvl[s], cnt * sizeof(float));
-    if (bins) memcpy(bins + off, h->p_bins[s], cnt * sizeof(int32_t));
+    const size_t n = h->n;
+    if (G == 1) {
+        const size_t off = (size_t)h->slot_w0[s] * n, cnt = (size_t)W * n;
+        memcpy(angles + off, h->p_ang[s], cnt * sizeof(float));
+        if (levels) memcpy(levels + off, h->p_lvl[s], cnt * sizeof(float));
+        if (bins) memcpy(bins + off, h->p_bins[s], cnt * sizeof(int32_t));
+    } else {
+        for (uint32_t i = 0; i < W; ++i) {
+            const size_t off = ((size_t)(h->slot_w0[s] + i) * G + g) * n;
+            for (size_t r = 0; r < n; ++r) {
+                angles[off + r] = h->p_ang[s][i * n + r];
+                if (levels) levels[off + r] = h->p_lvl[s][i * n + r];
+                if (bins) bins[off + r] = h->p_bins[s][i * n + r];
+            }
+        }
+    }
     h->slot_W[s] = 0;
 }
 
@@ -588,7 +762,7 @@ int download_host_slot(music_b200 *h, int s, uint32_t w0, uint32_t W, bool level
 
 extern "C" {
 
-int music_b200_version(void) { return 1; }
+int music_b200_version(void) { return 2; }
 
 const char *music_b200_last_error(const music_b200 *h)
 {
@@ -604,20 +778,41 @@ const char *music_b200_last_error(const music_b200 *h)
     return copy.c_str();
 }
 
-uint64_t music_b200_launch_count(const music_b200 *h) { return h ? h->launches.load() : 0; }
+uint64_t music_b200_launch_count(const music_b200 *h)
+{
+    if (!h) return 0;
+    uint64_t n = h->launches.load();
+    for (const music_b200 *c : h->kids) n += c->launches.load();
+    return n;
+}
 
 int music_b200_debug_fused_trace(music_b200 *h, long long *host_out, int max_ctas)
 {
+    if (h && !h->kids.empty()) return music_b200_debug_fused_trace(h->kids[0], host_out, max_ctas);  // multi-device handle: device 0 serves this entry
     if (!h || !host_out || !h->fused_trace) return MUSIC_B200_EINVAL;
     std::lock_guard<std::mutex> g(h->mutex);
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaDeviceSynchronize());
-    CU(h, cudaMemcpy(host_out, h->fused_trace, (size_t)std::min(max_ctas, 1024) * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(host_out, h->fused_trace, (size_t)std::min(max_ctas, 1024) * FZ_TRACE * sizeof(long long), cudaMemcpyDeviceToHost));
+    return MUSIC_B200_OK;
+}
+
+int music_b200_debug_fused8_stats(music_b200 *h, uint64_t *out2)
+{
+    if (h && !h->kids.empty()) return music_b200_debug_fused8_stats(h->kids[0], out2);
+    if (!h || !out2 || !h->f8_stats) return MUSIC_B200_EINVAL;
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    unsigned v[2];
+    CU(h, cudaMemcpy(v, h->f8_stats, sizeof v, cudaMemcpyDeviceToHost));
+    out2[0] = v[0];
+    out2[1] = v[1];
     return MUSIC_B200_OK;
 }
 
 int music_b200_set_stage_timing(music_b200 *h, int enable)
 {
+    if (h && !h->kids.empty()) return music_b200_set_stage_timing(h->kids[0], enable);  // multi-device handle: device 0 serves this entry
     if (!h) return MUSIC_B200_EINVAL;
     std::lock_guard<std::mutex> g(h->mutex);
     h->timing = enable != 0;
@@ -627,6 +822,7 @@ int music_b200_set_stage_timing(music_b200 *h, int enable)
 
 int music_b200_get_stage_times(music_b200 *h, double *ms4, uint64_t *chunks)
 {
+    if (h && !h->kids.empty()) return music_b200_get_stage_times(h->kids[0], ms4, chunks);  // multi-device handle: device 0 serves this entry
     if (!h || !ms4) return MUSIC_B200_EINVAL;
     std::lock_guard<std::mutex> g(h->mutex);
     CU(h, cudaSetDevice(h->device));
@@ -704,15 +900,20 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         if (const char *e = getenv("MUSIC_B200_SCAN")) h->scan_fast = strcmp(e, "general") != 0;
         if (const char *e = getenv("MUSIC_B200_FUSED")) h->fused = atoi(e) != 0;
         if (const char *e = getenv("MUSIC_B200_COVN")) h->covn = atoi(e) != 0;
-        if (const char *e = getenv("MUSIC_B200_EIG4")) h->eig_coop = strcmp(e, "lane") != 0;
+        if (const char *e = getenv("MUSIC_B200_EIG")) h->eig_mode = !strcmp(e, "jacobi") ? 1 : !strcmp(e, "jacobi1") ? 2 : 0;
+        if (const char *e = getenv("MUSIC_B200_MMA_FIN")) h->mma_fin_max = std::max(-1, std::min(8, atoi(e)));
         CU(h, cudaFuncSetAttribute(covN_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
         CU(h, cudaFuncSetAttribute(covN_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
+        CU(h, cudaFuncSetAttribute(music8_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F8_SMEM));
+        CU(h, cudaMalloc(&h->f8_stats, 2 * sizeof(unsigned)));
+        CU(h, cudaMemset(h->f8_stats, 0, 2 * sizeof(unsigned)));
         CU(h, cudaEventCreateWithFlags(&h->fused_done, cudaEventDisableTiming));
-        CU(h, cudaMalloc(&h->work_ctr, 2 * sizeof(unsigned)));
-        CU(h, cudaMemset(h->work_ctr, 0, 2 * sizeof(unsigned)));
+        CU(h, cudaMalloc(&h->work_ctr, 4 * sizeof(unsigned)));  // two self-resetting (tickets, finished CTAs) pairs
+        CU(h, cudaMemset(h->work_ctr, 0, 4 * sizeof(unsigned)));
+        if (const char *e = getenv("MUSIC_B200_HOSTREG")) h->hostreg = atoi(e) != 0;
         if (getenv("MUSIC_B200_TRACE")) {
-            CU(h, cudaMalloc(&h->fused_trace, 16 * sizeof(long long) * 1024));
-            CU(h, cudaMemset(h->fused_trace, 0, 16 * sizeof(long long) * 1024));
+            CU(h, cudaMalloc(&h->fused_trace, FZ_TRACE * sizeof(long long) * 1024));
+            CU(h, cudaMemset(h->fused_trace, 0, FZ_TRACE * sizeof(long long) * 1024));
         }
         CU(h, cudaFuncSetAttribute(music4_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
         CU(h, cudaFuncSetAttribute(music4_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
@@ -736,6 +937,13 @@ int music_b200_set_table(music_b200 *h, const float *table_c64)
     if (!h) return MUSIC_B200_EINVAL;
     if (!table_c64) return fail(h, MUSIC_B200_EINVAL, "array response table must not be NULL");
     std::lock_guard<std::mutex> g(h->mutex);
+    if (!h->kids.empty()) {  // multi-device handle: every device holds a full copy of the table
+        for (music_b200 *c : h->kids) {
+            const int rc = music_b200_set_table(c, table_c64);
+            if (rc) return fail(h, rc, "%s", music_b200_last_error(c));
+        }
+        return MUSIC_B200_OK;
+    }
     CU(h, cudaSetDevice(h->device));
     // Work enqueued by earlier process_device() calls may still be reading the current slot on
     // a caller stream; fill the other slot and flip.  (The slot being overwritten was retired
@@ -751,6 +959,7 @@ int music_b200_set_table(music_b200 *h, const float *table_c64)
 int music_b200_process_planar_device(music_b200 *h, const float *const *d_streams, uint32_t hop, uint32_t nwindows,
                                      float *d_angles, float *d_levels, float *d_spectrum, int32_t *d_bins, void *stream)
 {
+    if (h && !h->kids.empty()) return music_b200_process_planar_device(h->kids[0], d_streams, hop, nwindows, d_angles, d_levels, d_spectrum, d_bins, stream);  // multi-device handle: device 0 serves this entry
     if (!h) return MUSIC_B200_EINVAL;
     if (nwindows == 0) return MUSIC_B200_OK;
     if (!d_streams) return fail(h, MUSIC_B200_EINVAL, "d_streams must not be NULL");
@@ -771,6 +980,7 @@ int music_b200_process_planar_device(music_b200 *h, const float *const *d_stream
 int music_b200_process_planar_host(music_b200 *h, const float *const *streams, uint32_t hop, uint32_t nwindows,
                                    float *angles, float *levels, float *spectrum, int32_t *bins)
 {
+    if (h && !h->kids.empty()) return music_b200_process_planar_host(h->kids[0], streams, hop, nwindows, angles, levels, spectrum, bins);  // multi-device handle: device 0 serves this entry
     if (!h) return MUSIC_B200_EINVAL;
     if (nwindows == 0) return MUSIC_B200_OK;
     if (!streams || !angles) return fail(h, MUSIC_B200_EINVAL, "streams and angles must not be NULL");
@@ -830,6 +1040,7 @@ int music_b200_process_planar_host(music_b200 *h, const float *const *streams, u
 int music_b200_reduce_angles_device(music_b200 *h, const float *d_angles, const float *d_levels, uint32_t nwindows, int weighted,
                                     float *d_mean_deg, float *d_resultant, float *d_weight_sum, void *stream)
 {
+    if (h && !h->kids.empty()) return music_b200_reduce_angles_device(h->kids[0], d_angles, d_levels, nwindows, weighted, d_mean_deg, d_resultant, d_weight_sum, stream);  // multi-device handle: device 0 serves this entry
     if (!h) return MUSIC_B200_EINVAL;
     if (!d_angles || !d_mean_deg) return fail(h, MUSIC_B200_EINVAL, "d_angles and d_mean_deg must not be NULL");
     if (weighted && !d_levels) return fail(h, MUSIC_B200_EINVAL, "level weighting needs d_levels");
@@ -844,6 +1055,7 @@ int music_b200_reduce_angles_device(music_b200 *h, const float *d_angles, const 
 
 int music_b200_reduce_spectrum_device(music_b200 *h, const float *d_spectrum, uint32_t nwindows, float *d_mean, void *stream)
 {
+    if (h && !h->kids.empty()) return music_b200_reduce_spectrum_device(h->kids[0], d_spectrum, nwindows, d_mean, stream);  // multi-device handle: device 0 serves this entry
     if (!h) return MUSIC_B200_EINVAL;
     if (!d_spectrum || !d_mean) return fail(h, MUSIC_B200_EINVAL, "d_spectrum and d_mean must not be NULL");
     if (nwindows == 0) return fail(h, MUSIC_B200_EINVAL, "nwindows must be >= 1");
@@ -859,6 +1071,7 @@ int music_b200_reduce_spectrum_device(music_b200 *h, const float *d_spectrum, ui
 int music_b200_reduce_angles_host(music_b200 *h, const float *angles, const float *levels, uint32_t nwindows, int weighted,
                                   float *mean_deg, float *resultant, float *weight_sum)
 {
+    if (h && !h->kids.empty()) return music_b200_reduce_angles_host(h->kids[0], angles, levels, nwindows, weighted, mean_deg, resultant, weight_sum);  // multi-device handle: device 0 serves this entry
     if (!h) return MUSIC_B200_EINVAL;
     if (!angles || !mean_deg) return fail(h, MUSIC_B200_EINVAL, "angles and mean_deg must not be NULL");
     if (weighted && !levels) return fail(h, MUSIC_B200_EINVAL, "level weighting needs levels");
@@ -895,6 +1108,7 @@ int music_b200_reduce_angles_host(music_b200 *h, const float *angles, const floa
 
 int music_b200_reduce_spectrum_host(music_b200 *h, const float *spectrum, uint32_t nwindows, float *mean)
 {
+    if (h && !h->kids.empty()) return music_b200_reduce_spectrum_host(h->kids[0], spectrum, nwindows, mean);  // multi-device handle: device 0 serves this entry
     if (!h) return MUSIC_B200_EINVAL;
     if (!spectrum || !mean) return fail(h, MUSIC_B200_EINVAL, "spectrum and mean must not be NULL");
     if (nwindows == 0) return fail(h, MUSIC_B200_EINVAL, "nwindows must be >= 1");
@@ -924,6 +1138,10 @@ int music_b200_set_peak_mode(music_b200 *h, int mode, uint32_t exclusion_bins)
     if (mode != MUSIC_B200_PEAKS_TOP_BINS && mode != MUSIC_B200_PEAKS_LOCAL_MAXIMA) return fail(h, MUSIC_B200_EINVAL, "unknown peak mode %d", mode);
     if (exclusion_bins >= h->K) return fail(h, MUSIC_B200_EINVAL, "exclusion_bins must be < resolution");
     std::lock_guard<std::mutex> g(h->mutex);
+    for (music_b200 *c : h->kids) {
+        const int rc = music_b200_set_peak_mode(c, mode, exclusion_bins);
+        if (rc) return fail(h, rc, "%s", music_b200_last_error(c));
+    }
     h->peak_mode = mode;
     h->peak_excl = exclusion_bins;
     return MUSIC_B200_OK;
@@ -937,6 +1155,13 @@ int music_b200_set_geometry(music_b200 *h, const double *positions_xy, double wa
     for (uint32_t i = 0; i < 2 * h->m; ++i)
         if (!std::isfinite(positions_xy[i])) return fail(h, MUSIC_B200_EINVAL, "element positions must be finite");
     std::lock_guard<std::mutex> g(h->mutex);
+    if (!h->kids.empty()) {
+        for (music_b200 *c : h->kids) {
+            const int rc = music_b200_set_geometry(c, positions_xy, wavelength, guarded);
+            if (rc) return fail(h, rc, "%s", music_b200_last_error(c));
+        }
+        return MUSIC_B200_OK;
+    }
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaDeviceSynchronize());  // as in set_table(): the slot being rebuilt must be idle
     const int slot = h->cur_table ^ 1;
@@ -957,6 +1182,7 @@ int music_b200_get_table(music_b200 *h, float *table_c64)
 {
     if (!h) return MUSIC_B200_EINVAL;
     if (!table_c64) return fail(h, MUSIC_B200_EINVAL, "output table must not be NULL");
+    if (!h->kids.empty()) return music_b200_get_table(h->kids[0], table_c64);
     std::lock_guard<std::mutex> g(h->mutex);
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaMemcpy(table_c64, h->table[h->cur_table].c64, (size_t)h->K * h->m * 2 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -968,8 +1194,28 @@ int music_b200_process_device_ex(music_b200 *h, const float *d_in_c64, uint32_t 
                                  double *d_eigvals, void *stream)
 {
     if (!h) return MUSIC_B200_EINVAL;
+    if (!h->kids.empty()) {
+        // multi-device handle: the call goes to the child on whose device the input lives
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, d_in_c64) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return fail(h, MUSIC_B200_EINVAL, "d_in_c64 is not a device pointer");
+        }
+        for (music_b200 *c : h->kids)
+            if (c->device == at.device) {
+                const int rc = music_b200_process_device_ex(c, d_in_c64, nwindows, d_angles, d_levels, d_spectrum, d_bins, d_P64, d_R, d_eigvals, stream);
+                if (rc) fail(h, rc, "%s", music_b200_last_error(c));
+                return rc;
+            }
+        return fail(h, MUSIC_B200_EINVAL, "d_in_c64 lives on device %d, which this handle does not own", at.device);
+    }
     std::lock_guard<std::mutex> g(h->mutex);
+    NvtxRange range("music_b200_process_device");
     CU(h, cudaSetDevice(h->device));
+    if (h->gather_G > 0) {
+        if ((size_t)nwindows * h->gather_G * h->n > h->gather_cap) return fail(h, MUSIC_B200_EINVAL, "gather buffer holds %zu entries, the call needs %zu", h->gather_cap, (size_t)nwindows * h->gather_G * h->n);
+        ++h->gather_epoch;
+    }
     return enqueue_device(h, d_in_c64, nwindows, d_angles, d_levels, d_spectrum, d_bins, d_P64, d_R, d_eigvals,
                           static_cast<cudaStream_t>(stream), 0, true);
 }
@@ -988,54 +1234,255 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
     if (nwindows == 0) return MUSIC_B200_OK;
     if (!in_c64 || !angles) return fail(h, MUSIC_B200_EINVAL, "in_c64 and angles must not be NULL");
     std::lock_guard<std::mutex> g(h->mutex);
-    CU(h, cudaSetDevice(h->device));
-    // chunk: ~32 MiB of input per copy, so that H2D of chunk i+1 overlaps compute of chunk i
+    NvtxRange range("music_b200_process_host");
+    // lanes: the handle itself, or the per-device children of a multi-device handle; lane g takes the windows
+    // w = i * G + g (round-robin at window granularity) - every lane feeds its own PCIe link
+    music_b200 *self[1] = {h};
+    music_b200 *const *lanes = h->kids.empty() ? self : h->kids.data();
+    const uint32_t G = h->kids.empty() ? 1u : (uint32_t)h->kids.size();
     const size_t win_bytes = (size_t)h->nsamples * 2 * sizeof(float);
-    // (with the spectrum port connected a window also returns K floats: bound the chunk by the larger of the two, so that
-    // short windows on a fine grid do not blow up the spectrum staging)
+    // chunk: ~32 MiB of input per copy, so that H2D of chunk i+1 overlaps compute of chunk i (with the spectrum port
+    // connected a window also returns K floats: bound the chunk by the larger of the two)
     const size_t per_win = std::max(win_bytes, spectrum ? (size_t)h->K * sizeof(float) : (size_t)0);
+    const uint32_t per_lane = (nwindows + G - 1) / G;
     uint32_t chunk = (uint32_t)std::max<size_t>(SCAN_B, ((size_t)32 << 20) / per_win);
-    chunk = std::min(chunk, (nwindows + 1) / 2 > SCAN_B ? (nwindows + 1) / 2 : nwindows);
+    chunk = std::min(chunk, (per_lane + 1) / 2 > SCAN_B ? (per_lane + 1) / 2 : per_lane);
     chunk = std::max<uint32_t>(1, chunk);
-    h->slot_W[0] = h->slot_W[1] = 0;  // nothing pending from an earlier (possibly failed) call
-    int rc = ensure_host_staging(h, chunk, spectrum != nullptr);
-    if (rc) return rc;
-    // Each of the two copy streams computes in its own workspace slot, so H2D, kernels and D2H of
-    // consecutive chunks overlap freely (the path is PCIe-bound by ~100x, no sub-batch pipeline).
-    int it = 0;
-    rc = MUSIC_B200_OK;
-    for (uint32_t w0 = 0; w0 < nwindows && rc == MUSIC_B200_OK; w0 += chunk, ++it) {
-        const int s = it & 1;
-        const uint32_t W = std::min(chunk, nwindows - w0);
-        cudaStream_t st = h->streams[s];
-        if (it >= 2) {
-            CU_BREAK(h, rc, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
-            flush_host_slot(h, s, angles, levels, bins);
-        }
-        CU_BREAK(h, rc, cudaMemcpyAsync(h->d_in[s], in_c64 + (size_t)w0 * h->nsamples * 2, (size_t)W * win_bytes, cudaMemcpyHostToDevice, st));
-        rc = enqueue_device(h, h->d_in[s], W, h->d_ang[s], h->d_lvl[s], spectrum ? h->d_spec[s] : nullptr, h->d_bins[s],
-                            nullptr, nullptr, nullptr, st, s, false);
-        if (rc) break;
-        rc = download_host_slot(h, s, w0, W, levels != nullptr, bins != nullptr, st);
-        if (rc) break;
-        if (spectrum) CU_BREAK(h, rc, cudaMemcpyAsync(spectrum + (size_t)w0 * h->K, h->d_spec[s], (size_t)W * h->K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // pageable caller memory (GNU Radio's circular buffers, numpy arrays) is pinned once and found again on later calls
+    CU(h, cudaSetDevice(lanes[0]->device));
+    host_register(h, in_c64, (size_t)nwindows * win_bytes, true);
+    if (spectrum) host_register(h, spectrum, (size_t)nwindows * h->K * sizeof(float), false);
+    int rc = MUSIC_B200_OK;
+    for (uint32_t l = 0; l < G && rc == MUSIC_B200_OK; ++l) {
+        music_b200 *c = lanes[l];
+        if (cudaSetDevice(c->device) != cudaSuccess) { rc = fail(h, MUSIC_B200_ECUDA, "cudaSetDevice(%d) failed", c->device); break; }
+        c->slot_W[0] = c->slot_W[1] = 0;  // nothing pending from an earlier (possibly failed) call
+        rc = ensure_host_staging(c, chunk, spectrum != nullptr);
+        if (rc && c != h) fail(h, rc, "%s", std::string(c->error).c_str());
     }
-    cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
-    cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
-    if (rc || e0 != cudaSuccess || e1 != cudaSuccess) h->slot_W[0] = h->slot_W[1] = 0;  // nothing valid to hand out
-    if (rc) return rc;
-    if (e0 != cudaSuccess || e1 != cudaSuccess)
-        return fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
-    flush_host_slot(h, 0, angles, levels, bins);
-    flush_host_slot(h, 1, angles, levels, bins);
+    // Each of a lane's two copy streams computes in its own workspace slot and with its own ticket counter, so H2D,
+    // kernels and D2H of consecutive chunks overlap freely (the path is PCIe-bound by ~100x).
+    for (uint32_t it = 0; rc == MUSIC_B200_OK && (uint64_t)it * chunk < per_lane; ++it) {
+        const int s = (int)(it & 1);
+        for (uint32_t l = 0; l < G && rc == MUSIC_B200_OK; ++l) {
+            music_b200 *c = lanes[l];
+            const uint32_t Wl = l < nwindows ? (nwindows - l + G - 1) / G : 0;  // windows of this lane
+            const uint32_t i0 = it * chunk;
+            if (i0 >= Wl) continue;
+            const uint32_t W = std::min(chunk, Wl - i0);
+            cudaStream_t st = c->streams[s];
+            CU_BREAK(h, rc, cudaSetDevice(c->device));
+            if (it >= 2) {
+                CU_BREAK(h, rc, cudaStreamSynchronize(st));  // slot buffers free again (its D2H finished)
+                flush_host_slot(c, s, angles, levels, bins, G, l);
+            }
+            const float *src = in_c64 + ((size_t)i0 * G + l) * h->nsamples * 2;
+            {
+                NvtxRange r("music_b200: H2D");
+                if (G == 1) { CU_BREAK(h, rc, cudaMemcpyAsync(c->d_in[s], src, (size_t)W * win_bytes, cudaMemcpyHostToDevice, st)); }
+                else { CU_BREAK(h, rc, cudaMemcpy2DAsync(c->d_in[s], win_bytes, src, (size_t)G * win_bytes, win_bytes, W, cudaMemcpyHostToDevice, st)); }
+            }
+            {
+                NvtxRange r("music_b200: kernels");
+                rc = enqueue_device(c, c->d_in[s], W, c->d_ang[s], c->d_lvl[s], spectrum ? c->d_spec[s] : nullptr, c->d_bins[s],
+                                    nullptr, nullptr, nullptr, st, s, false);
+                if (rc && c != h) fail(h, rc, "%s", std::string(c->error).c_str());
+                if (rc) break;
+            }
+            NvtxRange r("music_b200: D2H");
+            rc = download_host_slot(c, s, i0, W, levels != nullptr, bins != nullptr, st);
+            if (rc && c != h) fail(h, rc, "%s", std::string(c->error).c_str());
+            if (rc) break;
+            if (spectrum) {
+                float *dst = spectrum + ((size_t)i0 * G + l) * h->K;
+                const size_t row = (size_t)h->K * sizeof(float);
+                if (G == 1) { CU_BREAK(h, rc, cudaMemcpyAsync(dst, c->d_spec[s], (size_t)W * row, cudaMemcpyDeviceToHost, st)); }
+                else { CU_BREAK(h, rc, cudaMemcpy2DAsync(dst, (size_t)G * row, c->d_spec[s], row, row, W, cudaMemcpyDeviceToHost, st)); }
+            }
+        }
+    }
+    // common tail, also after an error: every stream idle, nothing left pending in the slots
+    cudaError_t e_sync = cudaSuccess;
+    for (uint32_t l = 0; l < G; ++l) {
+        music_b200 *c = lanes[l];
+        cudaSetDevice(c->device);
+        for (int s = 0; s < 2; ++s) {
+            const cudaError_t e = cudaStreamSynchronize(c->streams[s]);
+            if (e != cudaSuccess && e_sync == cudaSuccess) e_sync = e;
+        }
+    }
+    if (rc == MUSIC_B200_OK && e_sync != cudaSuccess) rc = fail(h, MUSIC_B200_ECUDA, "stream sync failed: %s", cudaGetErrorString(e_sync));
+    for (uint32_t l = 0; l < G; ++l) {
+        music_b200 *c = lanes[l];
+        if (rc == MUSIC_B200_OK) {
+            flush_host_slot(c, 0, angles, levels, bins, G, l);
+            flush_host_slot(c, 1, angles, levels, bins, G, l);
+        } else {
+            c->slot_W[0] = c->slot_W[1] = 0;  // nothing valid to hand out
+        }
+    }
+    return rc;
+}
+
+int music_b200_create_multi(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsamples, uint32_t resolution,
+                            const float *table_c64, const int *devices, int ndev)
+{
+    if (!out) return fail(nullptr, MUSIC_B200_EINVAL, "out must not be NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > MAX_PEERS) return fail(nullptr, MUSIC_B200_EINVAL, "need 1..%d devices (got %d)", MAX_PEERS, ndev);
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, MUSIC_B200_EINVAL, "device %d listed twice", devices[i]);
+    music_b200 *h = new (std::nothrow) music_b200();
+    if (!h) return fail(nullptr, MUSIC_B200_ENOMEM, "out of host memory");
+    h->m = m; h->n = n; h->nsamples = nsamples; h->K = resolution; h->N = m ? nsamples / m : 0;
+    h->device = devices[0];
+    if (const char *e = getenv("MUSIC_B200_HOSTREG")) h->hostreg = atoi(e) != 0;
+    for (int i = 0; i < ndev; ++i) {
+        music_b200 *c = nullptr;
+        const int rc = music_b200_create(&c, m, n, nsamples, resolution, table_c64, devices[i]);  // (sets the create error text)
+        if (rc != MUSIC_B200_OK) {
+            music_b200_destroy(h);
+            return rc;
+        }
+        h->kids.push_back(c);
+    }
+    // peer access between every pair (the sharded device entry stores peak bins straight into the peers' buffers)
+    for (int i = 0; i < ndev; ++i) {
+        cudaSetDevice(devices[i]);
+        for (int j = 0; j < ndev; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e != cudaSuccess) cudaGetLastError();  // already enabled is fine
+            }
+        }
+    }
+    *out = h;
     return MUSIC_B200_OK;
+}
+
+int music_b200_device_count(const music_b200 *h) { return h ? (h->kids.empty() ? 1 : (int)h->kids.size()) : 0; }
+
+/* ---- fused all-gather of the peak bins across processes (one GPU per process) ---- */
+int music_b200_gather_create(music_b200 *h, uint32_t total_windows, unsigned char *ipc_handles /* [2][64] */)
+{
+    if (!h || !ipc_handles) return MUSIC_B200_EINVAL;
+    if (!h->kids.empty()) return fail(h, MUSIC_B200_EINVAL, "gather_create applies to single-device handles (a multi-device handle gathers in process_device_sharded)");
+    std::lock_guard<std::mutex> g(h->mutex);
+    CU(h, cudaSetDevice(h->device));
+    if (h->gather_buf) return fail(h, MUSIC_B200_EINVAL, "gather buffer already created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    const size_t elems = (size_t)total_windows * h->n;
+    CU(h, cudaMalloc(&h->gather_buf, std::max<size_t>(elems, 1) * sizeof(int32_t)));
+    CU(h, cudaMalloc(&h->gather_flags, MAX_PEERS * sizeof(unsigned)));
+    CU(h, cudaMemset(h->gather_buf, 0xff, std::max<size_t>(elems, 1) * sizeof(int32_t)));
+    CU(h, cudaMemset(h->gather_flags, 0, MAX_PEERS * sizeof(unsigned)));
+    h->gather_cap = elems;
+    cudaIpcMemHandle_t hb, hf;
+    CU(h, cudaIpcGetMemHandle(&hb, h->gather_buf));
+    CU(h, cudaIpcGetMemHandle(&hf, h->gather_flags));
+    memcpy(ipc_handles, &hb, 64);
+    memcpy(ipc_handles + 64, &hf, 64);
+    return MUSIC_B200_OK;
+}
+
+int music_b200_gather_attach(music_b200 *h, int nranks, int rank, const unsigned char *all_handles /* [nranks][2][64] */)
+{
+    if (!h || !all_handles) return MUSIC_B200_EINVAL;
+    if (nranks < 1 || nranks > MAX_PEERS || rank < 0 || rank >= nranks) return fail(h, MUSIC_B200_EINVAL, "need 1 <= nranks <= %d and 0 <= rank < nranks", MAX_PEERS);
+    std::lock_guard<std::mutex> g(h->mutex);
+    if (!h->gather_buf) return fail(h, MUSIC_B200_EINVAL, "call gather_create first");
+    CU(h, cudaSetDevice(h->device));
+    for (int p = 0; p < nranks; ++p) {
+        if (p == rank) {
+            h->peer_bins[p] = h->gather_buf;
+            h->peer_flags[p] = h->gather_flags;
+            continue;
+        }
+        cudaIpcMemHandle_t hb, hf;
+        memcpy(&hb, all_handles + (size_t)p * 128, 64);
+        memcpy(&hf, all_handles + (size_t)p * 128 + 64, 64);
+        void *pb = nullptr, *pf = nullptr;
+        CU(h, cudaIpcOpenMemHandle(&pb, hb, cudaIpcMemLazyEnablePeerAccess));
+        CU(h, cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_bins[p] = static_cast<int32_t *>(pb);
+        h->peer_flags[p] = static_cast<unsigned *>(pf);
+        h->peer_ipc[p] = true;
+    }
+    h->gather_G = nranks;
+    h->gather_rank = rank;
+    h->gather_epoch = 0;
+    return MUSIC_B200_OK;
+}
+
+int music_b200_gather_wait(music_b200 *h, void *stream)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    std::lock_guard<std::mutex> g(h->mutex);
+    if (h->gather_G <= 0 || !h->gather_flags) return fail(h, MUSIC_B200_EINVAL, "no gather attached");
+    CU(h, cudaSetDevice(h->device));
+    gather_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->gather_flags, h->gather_G, h->gather_epoch);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return MUSIC_B200_OK;
+}
+
+const int32_t *music_b200_gather_buffer(const music_b200 *h) { return h ? h->gather_buf : nullptr; }
+
+int music_b200_gather_read(music_b200 *h, int32_t *host_out, uint32_t count)
+{
+    if (!h || !host_out) return MUSIC_B200_EINVAL;
+    std::lock_guard<std::mutex> g(h->mutex);
+    if (!h->gather_buf || count > h->gather_cap) return fail(h, MUSIC_B200_EINVAL, "gather buffer holds %zu entries", h->gather_cap);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpy(host_out, h->gather_buf, (size_t)count * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return MUSIC_B200_OK;
+}
+
+/* ---- one call, G devices, inputs resident: shard g holds the windows w = i * G + g ---- */
+int music_b200_process_device_sharded(music_b200 *h, const float *const *d_in_c64, uint32_t nwindows_total, float *const *d_angles,
+                                      float *const *d_levels, int32_t *const *d_bins_all, void *const *streams)
+{
+    if (!h) return MUSIC_B200_EINVAL;
+    if (h->kids.empty()) return fail(h, MUSIC_B200_EINVAL, "process_device_sharded needs a handle from music_b200_create_multi");
+    if (!d_in_c64 || !d_angles) return fail(h, MUSIC_B200_EINVAL, "d_in_c64 and d_angles must not be NULL");
+    std::lock_guard<std::mutex> g(h->mutex);
+    NvtxRange range("music_b200_process_device_sharded");
+    const int G = (int)h->kids.size();
+    int rc = MUSIC_B200_OK;
+    for (int l = 0; l < G && rc == MUSIC_B200_OK; ++l) {
+        music_b200 *c = h->kids[l];
+        const uint32_t Wl = (uint32_t)l < nwindows_total ? (nwindows_total - l + G - 1) / G : 0;
+        if (!Wl) continue;
+        CU_BREAK(h, rc, cudaSetDevice(c->device));
+        // the scan epilogue of shard l stores its peak bins at stream position w = i * G + l of EVERY device's array
+        c->gather_G = d_bins_all ? G : 0;
+        c->gather_rank = l;
+        for (int p = 0; p < G; ++p) { c->peer_bins[p] = d_bins_all ? d_bins_all[p] : nullptr; c->peer_flags[p] = nullptr; }
+        rc = enqueue_device(c, d_in_c64[l], Wl, d_angles[l], d_levels ? d_levels[l] : nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            streams ? static_cast<cudaStream_t>(streams[l]) : nullptr, 0, false);
+        c->gather_G = 0;
+        if (rc) fail(h, rc, "%s", std::string(c->error).c_str());
+    }
+    return rc;
 }
 
 void music_b200_destroy(music_b200 *h)
 {
     if (!h) return;
+    for (music_b200 *c : h->kids) music_b200_destroy(c);
+    h->kids.clear();
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    for (const music_b200::HostReg &r : h->hostregs) cudaHostUnregister(reinterpret_cast<void *>(r.base));
+    h->hostregs.clear();
+    for (int p = 0; p < MAX_PEERS; ++p)
+        if (h->peer_ipc[p]) { cudaIpcCloseMemHandle(h->peer_bins[p]); cudaIpcCloseMemHandle(h->peer_flags[p]); }
+    cudaFree(h->gather_buf);
+    cudaFree(h->gather_flags);
+    cudaGetLastError();
     free_host_staging(h);
     for (int i = 0; i < NSLOT; ++i) {
         Workspace &ws = h->ws[i];
@@ -1047,6 +1494,7 @@ void music_b200_destroy(music_b200 *h)
     if (h->s_scan) cudaStreamDestroy(h->s_scan);
     if (h->ev_in) cudaEventDestroy(h->ev_in);
     cudaFree(h->fused_trace);
+    cudaFree(h->f8_stats);
     cudaFree(h->work_ctr);
     cudaFree(h->steer_pos); cudaFree(h->steer_count); cudaFree(h->steer_list); cudaFree(h->steer_vals);
     if (h->fused_done) cudaEventDestroy(h->fused_done);

@@ -1,13 +1,14 @@
 // music_fused.cuh - FUSED persistent kernel for the headline shape class (M = 4 antennas, n = 1
-// source, peak outputs only): covariance + eigendecomposition + pseudospectrum scan + peak pick in
+// source, peak outputs only): covariance + eigenvectors + pseudospectrum scan + peak pick in
 // ONE launch, one CTA per SM, warp-specialised.  R and the eigenvectors never leave shared memory.
 //
 //   warps 0..7   covariance (FP64 pipe): per-warp TMA ring exactly as cov4_tma_kernel; a finished
-//                window's R is pushed into a 64-slot shared-memory queue (in-order publish).
-//   warp  8      eigensolver: four lanes per queued window (8 windows per round, herm_eig4_coop in
-//                music_kernels.cuh; bit-identical to the one-lane herm_eig_body<4>, which
-//                MUSIC_B200_EIG4=lane selects), eigenvectors written next to the queue slot.
-//   warps 9..15  pseudospectrum scan + peak pick, up to 8 windows per pass (two sweeps of the table):
+//                window's R is written to a 64-slot shared-memory queue and marked ready (per-slot flag).
+//   warp  8      eigenvectors, four lanes per queued window (8 windows per round): principal eigenvector by
+//                repeated squaring + Householder basis of its complement (music_eig4p.cuh, ~2 k cycles per
+//                round); windows that do not converge (noise only, NaN) go through the full Jacobi solver
+//                (herm_eig4_coop in music_kernels.cuh, ~26 k cycles), which MUSIC_B200_EIG=jacobi selects for all.
+//   warps 9..15  pseudospectrum scan + peak pick, 8 windows per pass (two sweeps of the table):
 //                  1. SCREEN on the tensor cores: c_k = e_s^H a_k for all bins k and the 4 windows as a
 //                     [bins x 8] x [8 x 8] product in 3xTF32 (mma.sync m16n8k8, hi/lo split of both
 //                     operands, fp32 accumulate), d~_k = ||a_k||^2 - |c_k|^2 in fp32.  The FP64 pipe -
@@ -21,6 +22,15 @@
 //                     Typically 2-60 bins per window; if more than FZ_CMAX bins of a window survive (flat
 //                     spectra, e.g. an all-zero window) every bin of that window is evaluated in fp64 instead.
 //                The result is therefore bit-identical to an all-fp64 scan.
+//   DRAIN        A tensor-core pass has a latency of ~27 k cycles whatever it holds, and that latency (plus the
+//                eigensolver's) used to be the tail of the launch: 58 k cycles per CTA with HBM idle.  Once the
+//                window tickets have run out and more than FZ_MMA_FIN covariance warps are done, no new pass is
+//                started: every warp that has nothing left to do - covariance warps as they finish, the scan warps
+//                after their last pass, the eigenvector warp at the end - becomes a drain worker and takes
+//                (group of <= 4 windows, 1/8 of the bins) units of an all-fp64 scan (scan_bin, the unfused
+//                scan_peak1_kernel's hot loop; the FP64 pipe is free by then), merged per group in fixed order by
+//                the warp that finishes the group's last unit.  Same formula, same tie rule: bit-identical to the
+//                tensor-core path, at ~1.2 k cycles per window instead of a 27 k-cycle pass.
 //
 // Screen error bound.  a is stored in fp32 exactly (the block's table IS complex64) and split at run
 // time by truncation: a_hi = a & ~0x1fff (|a - a_hi| < 2^-10|a|), a_lo = (a - a_hi) & ~0x1fff (the
@@ -36,6 +46,7 @@
 // window except the optional spectrum port).
 #pragma once
 #include "music_kernels.cuh"
+#include "music_eig4p.cuh"
 #include "music_planar.cuh"
 
 namespace music {
@@ -56,34 +67,55 @@ constexpr int FZ_TILE_BYTES = (FZ_BINS / 16) * FZ_FRAG_BYTES + FZ_BINS * 4;  // 
 constexpr int FZ_CMAX = 256;    // exact candidates kept per window before falling back to a full fp64 scan
 constexpr float FZ_B = 3.0517578125e-05f;  // 2^-15, see "Screen error bound"
 
+constexpr int FZ_TRACE = 32;    // int64 trace words per CTA (MUSIC_B200_TRACE=1)
+constexpr int FZ_DG = 4;         // windows per drain group (= scan_bin's windows per thread)
+constexpr int FZ_NCH = 8;        // bin chunks per drain group: (group, chunk) is the unit a drain worker (one warp) takes
+constexpr int FZ_NGS = 4;        // drain groups in flight
+
 struct FusedCtl {               // shared-memory control block
-    unsigned cov_seq;           // tickets handed to covariance warps
-    volatile unsigned cov_pub;  // windows whose R is in the queue
+    unsigned cov_seq;           // queue sequence numbers handed to finished covariances (atomic)
+    unsigned lock;              // spin lock: claim, scan_done, drain group slots
     volatile unsigned eig_done; // windows whose eigenvectors are in the queue
-    volatile unsigned scan_done;// windows fully processed (queue slot free)
+    volatile unsigned scan_done;// every window below this is finished (its queue slot is free)
     volatile unsigned cov_finished;  // covariance warps that ran out of windows
     volatile unsigned batch_start, batch_cnt;
-    unsigned pad;
+    volatile unsigned claim;    // windows below this were handed to a tensor-core pass or to a drain group
+    volatile unsigned tout;     // the global ticket counter has run out
+    volatile unsigned mma_off;  // no further tensor-core passes: the drain workers take what is left
+    volatile int dg_open;       // drain group currently handing out chunks (-1: none)
+    unsigned drained_windows;   // statistics (trace)
+};
+struct DrainGroup {
+    volatile unsigned gs;       // first queue sequence number of the group
+    volatile int gc;            // windows in the group (1..FZ_DG)
+    unsigned next_chunk, done;  // chunks handed out / finished
+    volatile int busy;
+    int pad[3];
 };
 
 constexpr size_t FZ_OFF_TBAR = 512;     // uint64 tfull[FZ_TS], tempty[FZ_TS]
 constexpr size_t FZ_OFF_WRING = 768;    // int wring[FZ_COV_WARPS][8]: window ids claimed by each covariance warp
-constexpr size_t FZ_OFF_CTL = 1024;
+constexpr size_t FZ_OFF_CTL = 1024;     // FusedCtl (64 B)
 constexpr size_t FZ_OFF_WIN = 1088;     // int qwin[FZ_Q]
 constexpr size_t FZ_OFF_RMIN = 1344;    // float redmin[FZ_SCAN_WARPS][FZ_WPT]
 constexpr size_t FZ_OFF_CCNT = 1568;    // int cand_cnt[FZ_WPT]
 constexpr size_t FZ_OFF_CBIN = 1664;    // int cand_bin[FZ_WPT][FZ_CMAX]
 constexpr size_t FZ_OFF_RED = 9856;     // double redP[FZ_SCAN_WARPS]; int redk[FZ_SCAN_WARPS]  (fallback scan)
 constexpr size_t FZ_OFF_BEST = 9984;    // u64 bestP[FZ_WPT]; int bestk[FZ_WPT]; int admitted[FZ_WPT]
-constexpr size_t FZ_OFF_RQ = 10240;                           // double Rq[FZ_Q][32]
+constexpr size_t FZ_OFF_QRDY = 10112;   // unsigned qready[FZ_Q]: sequence number + 1 of the R held by the slot
+constexpr size_t FZ_OFF_QDONE = FZ_OFF_QRDY + 4 * FZ_Q;    // unsigned qdone[FZ_Q]: the slot's window is finished
+constexpr size_t FZ_OFF_DGRP = FZ_OFF_QDONE + 4 * FZ_Q;    // DrainGroup grp[FZ_NGS]
+constexpr size_t FZ_OFF_DRES = FZ_OFF_DGRP + 32 * FZ_NGS;  // double resP[FZ_NGS][FZ_NCH][FZ_DG]; int resk[...]
+constexpr size_t FZ_OFF_RQ = (FZ_OFF_DRES + 12 * FZ_NGS * FZ_NCH * FZ_DG + 255) / 256 * 256;  // double Rq[FZ_Q][32]
 constexpr size_t FZ_OFF_VQ = FZ_OFF_RQ + (size_t)FZ_Q * 256;  // double Vq[FZ_Q][32]
 constexpr size_t FZ_OFF_TBL = FZ_OFF_VQ + (size_t)FZ_Q * 256; // FZ_TS table tiles
 constexpr size_t FZ_OFF_RING = (FZ_OFF_TBL + (size_t)FZ_TS * FZ_TILE_BYTES + 127) / 128 * 128;
 constexpr size_t FZ_SMEM = FZ_OFF_RING + (size_t)FZ_COV_WARPS * FZ_STAGES * COV_CHUNK;
+static_assert(sizeof(FusedCtl) <= 64 && sizeof(DrainGroup) == 32, "control block layout");
 static_assert(FZ_COV_WARPS * FZ_STAGES * 8 <= FZ_OFF_TBAR, "covariance barriers overlap the table barriers");
 static_assert(FZ_OFF_RMIN + 4 * FZ_SCAN_WARPS * FZ_WPT <= FZ_OFF_CCNT && FZ_OFF_CCNT + 4 * FZ_WPT <= FZ_OFF_CBIN &&
                   FZ_OFF_CBIN + 4 * FZ_WPT * FZ_CMAX <= FZ_OFF_RED && FZ_OFF_RED + 12 * FZ_SCAN_WARPS <= FZ_OFF_BEST &&
-                  FZ_OFF_BEST + 16 * FZ_WPT <= FZ_OFF_RQ,
+                  FZ_OFF_BEST + 16 * FZ_WPT <= FZ_OFF_QRDY,
               "scan scratch layout");
 static_assert(FZ_SMEM <= 227 * 1024, "fused kernel shared memory");
 constexpr int FZ_CPT = (FZ_TILE_BYTES / 16 + FZ_SCAN_THREADS - 1) / FZ_SCAN_THREADS;  // 16-byte copies per thread and tile
@@ -168,6 +200,164 @@ __device__ __forceinline__ double fused_exact_P(const float *__restrict__ tab_c6
     return 1.0 / d;
 }
 
+// ---- shared-memory spin lock (one lane per warp contends) ----
+__device__ __forceinline__ void fz_lock(FusedCtl *ctl)
+{
+    while (atomicCAS(&ctl->lock, 0u, 1u) != 0u) {}
+    __threadfence_block();
+}
+__device__ __forceinline__ void fz_unlock(FusedCtl *ctl)
+{
+    __threadfence_block();
+    atomicExch(&ctl->lock, 0u);
+}
+
+// peak of one window -> the block's outputs (reference :134, :153-154; (0, 0) initial pair :95)
+__device__ __forceinline__ void fused_write_peak(const PeakOut &out, const size_t o, const int kk, const double P, const int K)
+{
+    if (kk >= 0) {
+        out.angles[o] = (float)((double)kk * 360.0 / (double)K);
+        if (out.levels) out.levels[o] = (float)P;
+    } else {
+        out.angles[o] = 0.f;
+        if (out.levels) out.levels[o] = 0.f;
+    }
+    peak_store_bin(out, o, kk);
+}
+
+// windows [start, start + cnt) are finished: mark their queue slots and advance scan_done over every finished slot
+// (tensor-core passes and drain groups complete out of order).  One thread.
+__device__ __forceinline__ void fused_retire(unsigned char *smem, const unsigned start, const unsigned cnt)
+{
+    FusedCtl *ctl = reinterpret_cast<FusedCtl *>(smem + FZ_OFF_CTL);
+    volatile unsigned *qdone = reinterpret_cast<volatile unsigned *>(smem + FZ_OFF_QDONE);
+    __threadfence_block();
+    fz_lock(ctl);
+    for (unsigned w = 0; w < cnt; ++w) qdone[(start + w) % FZ_Q] = 1u;
+    unsigned sd = ctl->scan_done;
+    while (sd != ctl->claim && qdone[sd % FZ_Q]) { qdone[sd % FZ_Q] = 0u; ++sd; }
+    ctl->scan_done = sd;
+    fz_unlock(ctl);
+}
+
+// Drain worker (a whole warp; see the file header): takes (group, bin chunk) units of an all-fp64 scan until every
+// window of this CTA has been handed out.  soa: the fp64 steering table of the unfused kernels ([tile][2M+1][TILE],
+// padding rows ||a||^2 = +inf).  Returns the number of units this warp processed.
+__device__ __noinline__ int fused_drain_worker(unsigned char *smem, const double *__restrict__ soa, const int K, const PeakOut out)
+{
+    FusedCtl *ctl = reinterpret_cast<FusedCtl *>(smem + FZ_OFF_CTL);
+    DrainGroup *grp = reinterpret_cast<DrainGroup *>(smem + FZ_OFF_DGRP);
+    double *resP = reinterpret_cast<double *>(smem + FZ_OFF_DRES);
+    int *resk = reinterpret_cast<int *>(smem + FZ_OFF_DRES + 8 * FZ_NGS * FZ_NCH * FZ_DG);
+    const int *qwin = reinterpret_cast<const int *>(smem + FZ_OFF_WIN);
+    const uint32_t Vq0 = smem_u32(smem + FZ_OFF_VQ);
+    const int lane = threadIdx.x & 31;
+    const int CB = (K + FZ_NCH * 32 - 1) / (FZ_NCH * 32) * 32;  // bins per chunk
+    const int Kpad = (K + TILE - 1) / TILE * TILE;
+    int units = 0;
+    for (;;) {
+        int slot = -1, chunk = 0, gc = 0;
+        unsigned gs = 0;
+        if (lane == 0) {
+            for (;;) {
+                bool all_done = false;
+                fz_lock(ctl);
+                const int cur = ctl->dg_open;
+                if (cur >= 0 && grp[cur].next_chunk < (unsigned)FZ_NCH) {
+                    slot = cur; chunk = (int)grp[cur].next_chunk++; gs = grp[cur].gs; gc = grp[cur].gc;
+                } else if (ctl->mma_off) {
+                    const unsigned start = ctl->claim, avail = ctl->eig_done - start;
+                    if (avail > 0) {
+                        int f = -1;
+                        for (int i = 0; i < FZ_NGS; ++i)
+                            if (!grp[i].busy) { f = i; break; }
+                        if (f >= 0) {
+                            gc = (int)min(avail, (unsigned)FZ_DG);
+                            grp[f].gs = start; grp[f].gc = gc; grp[f].next_chunk = 1u; grp[f].done = 0u; grp[f].busy = 1;
+                            ctl->claim = start + gc;
+                            ctl->dg_open = f;
+                            ctl->drained_windows += gc;
+                            slot = f; chunk = 0; gs = start;
+                        }
+                    } else {
+                        all_done = ctl->cov_finished == (unsigned)FZ_COV_WARPS &&
+                                   ctl->eig_done == *reinterpret_cast<volatile unsigned *>(&ctl->cov_seq);
+                    }
+                }
+                fz_unlock(ctl);
+                if (slot >= 0) break;
+                if (all_done) { slot = -2; break; }
+                __nanosleep(100);
+            }
+        }
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot < 0) return units;
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        gc = __shfl_sync(0xffffffffu, gc, 0);
+        gs = __shfl_sync(0xffffffffu, gs, 0);
+        ++units;
+        uint32_t ev[FZ_DG];
+#pragma unroll
+        for (int b = 0; b < FZ_DG; ++b) ev[b] = Vq0 + 256u * ((gs + (unsigned)min(b, gc - 1)) % FZ_Q);
+        PeakState<FZ_DG> ps;
+        ps.reset();
+        const int k1 = min((chunk + 1) * CB, Kpad);
+        for (int k = chunk * CB + lane; k < k1; k += 32) {
+            const double *tb = soa + (size_t)(k / TILE) * 9 * TILE + (k % TILE);
+            double ar[4], ai[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ar[i] = __ldg(tb + (size_t)(2 * i) * TILE);
+                ai[i] = __ldg(tb + (size_t)(2 * i + 1) * TILE);
+            }
+            const double na = __ldg(tb + (size_t)8 * TILE);
+            scan_bin<4, FZ_DG>(ar, ai, na, k, ev, ps);
+        }
+        // per-window merge over the lanes, order (P desc, bin asc)
+#pragma unroll
+        for (int b = 0; b < FZ_DG; ++b) {
+            int kk = ps.bestk[b];
+            double P = kk >= 0 ? 1.0 / ps.bestd[b] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double Po = __shfl_xor_sync(0xffffffffu, P, o);
+                const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
+                if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
+            }
+            if (lane == 0) {
+                resP[(slot * FZ_NCH + chunk) * FZ_DG + b] = P;
+                resk[(slot * FZ_NCH + chunk) * FZ_DG + b] = kk;
+            }
+        }
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = atomicAdd(&grp[slot].done, 1u) == (unsigned)FZ_NCH - 1 ? 1 : 0;
+            __threadfence_block();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            // this warp finished the group's last unit: merge the chunks in ascending order (lane b <-> window b)
+            if (lane < gc) {
+                double P = resP[(slot * FZ_NCH) * FZ_DG + lane];
+                int kk = resk[(slot * FZ_NCH) * FZ_DG + lane];
+                for (int c = 1; c < FZ_NCH; ++c) {
+                    const double Pc = resP[(slot * FZ_NCH + c) * FZ_DG + lane];
+                    const int kc = resk[(slot * FZ_NCH + c) * FZ_DG + lane];
+                    if (peak_better(Pc, kc, P, kk)) { P = Pc; kk = kc; }
+                }
+                fused_write_peak(out, (size_t)qwin[(gs + lane) % FZ_Q], kk, P, K);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                fused_retire(smem, gs, (unsigned)gc);
+                grp[slot].busy = 0;  // (results were read above; a new group may reuse the slot)
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // PLANAR = true: the window is read from four per-antenna streams (music_planar.cuh) - window w = snapshots
 // [first_snapshot + w * hop, ... + N) of each stream - by four 1 KiB bulk copies per stage instead of one 4 KiB copy;
 // the stage then holds [antenna][128 snapshots] and a lane gathers its snapshot with four LDS.64.  Requires 16-byte
@@ -179,7 +369,10 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     const float *__restrict__ tab_c64 /* [K][4] complex64 */, const float *__restrict__ na_max_p, int W, int N,
                     int K, PeakOut out, unsigned *__restrict__ work_ctr /* [0]: window tickets, [1]: finished CTAs; both zero between launches */,
                     long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */,
-                    const int eig_coop /* 1: four lanes per window in the eigensolver warp, 0: one lane per window */)
+                    const int eig_mode /* 0: principal eigenvector by squaring (Jacobi fallback), 1: Jacobi with four lanes per window, 2: Jacobi with one lane per window */,
+                    const double *__restrict__ soa /* fp64 steering table of the unfused kernels (drain workers) */,
+                    const GatherFlags gather_flags /* epoch flags of the fused bins all-gather (out.npeer > 0) */,
+                    const int mma_fin_max /* tensor-core passes start only while at most this many covariance warps are done; < 0: never */)
 {
     const long long t_start = clock64();
     unsigned long long g_start = 0;
@@ -187,13 +380,20 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
     extern __shared__ __align__(128) unsigned char fz_smem[];
     FusedCtl *ctl = reinterpret_cast<FusedCtl *>(fz_smem + FZ_OFF_CTL);
     int *qwin = reinterpret_cast<int *>(fz_smem + FZ_OFF_WIN);
+    volatile unsigned *qready = reinterpret_cast<volatile unsigned *>(fz_smem + FZ_OFF_QRDY);
     double *Rq = reinterpret_cast<double *>(fz_smem + FZ_OFF_RQ);
     double *Vq = reinterpret_cast<double *>(fz_smem + FZ_OFF_VQ);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (threadIdx.x < FZ_Q) {
+        reinterpret_cast<unsigned *>(fz_smem + FZ_OFF_QRDY)[threadIdx.x] = 0u;
+        reinterpret_cast<unsigned *>(fz_smem + FZ_OFF_QDONE)[threadIdx.x] = 0u;
+    }
+    if (threadIdx.x < FZ_NGS * 8) reinterpret_cast<unsigned *>(fz_smem + FZ_OFF_DGRP)[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
-        ctl->cov_seq = 0; ctl->cov_pub = 0; ctl->eig_done = 0; ctl->scan_done = 0; ctl->cov_finished = 0;
-        ctl->batch_start = 0; ctl->batch_cnt = 0;
+        ctl->cov_seq = 0; ctl->lock = 0; ctl->eig_done = 0; ctl->scan_done = 0; ctl->cov_finished = 0;
+        ctl->batch_start = 0; ctl->batch_cnt = 0; ctl->claim = 0; ctl->tout = 0; ctl->mma_off = mma_fin_max < 0 ? 1u : 0u;
+        ctl->dg_open = -1; ctl->drained_windows = 0;
         const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR);
         for (int s = 0; s < FZ_TS; ++s) {
             mbar_init(tb0 + 8 * s, FZ_SCAN_THREADS);            // tfull: one cp.async-completion arrival per scan thread
@@ -229,6 +429,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
         auto claim = [&]() {
             const unsigned tkt = atomicAdd(ctr, 1u);
             iw = tkt < (unsigned)W ? (int)tkt : -1;
+            if (iw < 0) ctl->tout = 1u;
             wring[wr & 7] = iw;
             ++wr;
         };
@@ -317,41 +518,52 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                         e += 2;
                     }
                 qwin[seq % FZ_Q] = wcur;
-                while (ctl->cov_pub != seq) {}  // publish in ticket order
                 __threadfence_block();
-                ctl->cov_pub = seq + 1;
+                qready[seq % FZ_Q] = seq + 1u;  // per-slot ready flag: no ordering between the covariance warps
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.0;
         }
         if (lane == 0) {
+            __threadfence_block();
             const unsigned fin = atomicAdd((unsigned *)&ctl->cov_finished, 1u);
-            if (dbg && fin == (unsigned)FZ_COV_WARPS - 1) dbg[blockIdx.x * 16 + 0] = clock64() - t_start;  // last covariance warp
-            if (dbg && fin == 0) dbg[blockIdx.x * 16 + 1] = clock64() - t_start;                           // first one
+            if (dbg && fin == (unsigned)FZ_COV_WARPS - 1) dbg[blockIdx.x * FZ_TRACE + 0] = clock64() - t_start;  // last covariance warp
+            if (dbg && fin == 0) dbg[blockIdx.x * FZ_TRACE + 1] = clock64() - t_start;                           // first one
         }
+        __syncwarp();
+        fused_drain_worker(fz_smem, soa, K, out);
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
-        long long eig_busy = 0, eig_rounds = 0;
+        long long eig_busy = 0, eig_rounds = 0, eig_jacobi = 0;
         for (;;) {
             const unsigned done = ctl->eig_done;
-            const unsigned avail = ctl->cov_pub - done;
+            // ready windows in queue order: slot (done + i) holds sequence number done + i iff its flag says so
+            const bool rdy = lane < 8 && qready[(done + lane) % FZ_Q] == done + lane + 1u;
+            const unsigned mask = __ballot_sync(0xffffffffu, rdy);
+            const unsigned avail = (unsigned)__ffs(~mask) - 1u;  // leading run of ready slots (0..8)
             if (avail == 0) {
-                if (ctl->cov_finished == (unsigned)FZ_COV_WARPS && ctl->cov_pub == done) break;
-                __nanosleep(200);
+                if (ctl->cov_finished == (unsigned)FZ_COV_WARPS && done == *reinterpret_cast<volatile unsigned *>(&ctl->cov_seq)) break;
+                __nanosleep(100);
                 continue;
             }
             __threadfence_block();
             const long long t0 = clock64();
             unsigned cnt;
-            if (eig_coop) {
-                // four lanes per window, 8 windows per round: a third of the one-lane solver's latency, and that
-                // latency is what the last windows of a launch wait for
+            if (eig_mode <= 1) {
                 cnt = min(avail, 8u);
                 const unsigned grp = (unsigned)lane >> 2;
                 const unsigned slot = (done + min(grp, cnt - 1)) % FZ_Q;
-                herm_eig4_coop(Rq + (size_t)slot * 32, Vq + (size_t)slot * 32, grp < cnt, lane & 3);
+                bool jac = grp < cnt;  // windows the Jacobi solver must take
+                if (eig_mode == 0) {  // (every lane must make the call: it shuffles and synchronises over the whole warp)
+                    const bool solved = eig4_principal_coop(Rq + (size_t)slot * 32, Vq + (size_t)slot * 32, jac, lane & 3);
+                    jac = jac && !solved;
+                }
+                if (__any_sync(0xffffffffu, jac)) {
+                    herm_eig4_coop(Rq + (size_t)slot * 32, Vq + (size_t)slot * 32, jac, lane & 3);
+                    ++eig_jacobi;
+                }
             } else {
-                cnt = min(avail, 32u);
+                cnt = min(avail, 8u);
                 if ((unsigned)lane < cnt) {
                     const unsigned slot = (done + lane) % FZ_Q;
                     herm_eig_body<4, true>(Rq + (size_t)slot * 32, nullptr, Vq + (size_t)slot * 32, 4);
@@ -365,10 +577,12 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             ++eig_rounds;
         }
         if (dbg && lane == 0) {
-            dbg[blockIdx.x * 16 + 8] = clock64() - t_start;
-            dbg[blockIdx.x * 16 + 9] = eig_busy;
-            dbg[blockIdx.x * 16 + 10] = eig_rounds;
+            dbg[blockIdx.x * FZ_TRACE + 8] = clock64() - t_start;
+            dbg[blockIdx.x * FZ_TRACE + 9] = eig_busy;
+            dbg[blockIdx.x * FZ_TRACE + 10] = eig_rounds;
+            dbg[blockIdx.x * FZ_TRACE + 19] = eig_jacobi;
         }
+        fused_drain_worker(fz_smem, soa, K, out);
     } else {
         // ================= scan warps =================
         const int st = threadIdx.x - 32 * (FZ_COV_WARPS + 1);  // 0..223
@@ -389,17 +603,29 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
 
         for (;;) {
             if (st == 0) {
-                // A pass streams the whole table from L2 once, so it waits for FZ_WPT windows unless the
-                // covariance and eigensolver stages have drained (then it takes what is left).
-                unsigned start, cnt;
+                // A pass streams the whole table from L2 once and costs ~27 k cycles whatever it holds, so it takes exactly
+                // FZ_WPT windows, and none is started once the launch is running out (see DRAIN in the file header).
+                unsigned start = 0, cnt = 0;
                 for (;;) {
-                    start = ctl->scan_done;
+                    bool stop = false;
+                    fz_lock(ctl);
+                    start = ctl->claim;
                     const unsigned avail = ctl->eig_done - start;
-                    if (avail >= (unsigned)FZ_WPT) { cnt = FZ_WPT; break; }
-                    const bool drained = ctl->cov_finished == (unsigned)FZ_COV_WARPS && ctl->cov_pub == ctl->eig_done;
-                    if (drained) { cnt = min(ctl->eig_done - start, (unsigned)FZ_WPT); break; }  // may be 0: all done
+                    const int fin = (int)ctl->cov_finished;
+                    if (ctl->mma_off) {
+                        stop = true;
+                    } else if (avail >= (unsigned)FZ_WPT && fin <= mma_fin_max) {
+                        cnt = FZ_WPT;
+                        ctl->claim = start + cnt;
+                    } else if ((ctl->tout && fin > mma_fin_max) || fin == FZ_COV_WARPS) {
+                        ctl->mma_off = 1u;
+                        stop = true;
+                    }
+                    fz_unlock(ctl);
+                    if (cnt || stop) break;
                     __nanosleep(200);
                 }
+                if (dbg && cnt == 0) dbg[blockIdx.x * FZ_TRACE + 16] = clock64() - t_start;  // when the tensor-core passes ended
                 ctl->batch_start = start;
                 ctl->batch_cnt = cnt;
                 __threadfence_block();
@@ -606,7 +832,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     out.angles[o] = 0.f;                                      // (0,0) initial pair, reference :95
                     if (out.levels) out.levels[o] = 0.f;
                 }
-                if (out.bins) out.bins[o] = kk;
+                peak_store_bin(out, o, kk);
             }
             if (dbg && st == 0) scan_ncand += pre[FZ_WPT];
             // ---- fallback: too many candidates (flat spectrum) -> every bin in fp64 ----
@@ -638,45 +864,54 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                         out.angles[o] = 0.f;
                         if (out.levels) out.levels[o] = 0.f;
                     }
-                    if (out.bins) out.bins[o] = kk;
+                    peak_store_bin(out, o, kk);
                     ++scan_fallbacks;
                 }
                 bar_sync_scan();
             }
             if (dbg) scan_exact += clock64() - te0;
             bar_sync_scan();  // scratch and the queue slots may be reused from here on
-            if (st == 0) {
-                __threadfence_block();
-                ctl->scan_done = start + cnt;
-            }
+            if (st == 0) fused_retire(fz_smem, start, cnt);
             scan_busy += clock64() - t0;
             ++scan_passes;
         }
         if (dbg && st == 0) {
-            dbg[blockIdx.x * 16 + 11] = clock64() - t_start;
-            dbg[blockIdx.x * 16 + 12] = scan_busy;
-            dbg[blockIdx.x * 16 + 13] = scan_passes;
-            dbg[blockIdx.x * 16 + 14] = scan_exact;
-            dbg[blockIdx.x * 16 + 15] = scan_fallbacks;
-            dbg[blockIdx.x * 16 + 7] = scan_ncand;
-            dbg[blockIdx.x * 16 + 4] = tr_issue;  // (overwrite covariance warps 4..6 slots)
-            dbg[blockIdx.x * 16 + 5] = tr_full;
-            dbg[blockIdx.x * 16 + 6] = tr_comp;
+            dbg[blockIdx.x * FZ_TRACE + 11] = clock64() - t_start;
+            dbg[blockIdx.x * FZ_TRACE + 12] = scan_busy;
+            dbg[blockIdx.x * FZ_TRACE + 13] = scan_passes;
+            dbg[blockIdx.x * FZ_TRACE + 14] = scan_exact;
+            dbg[blockIdx.x * FZ_TRACE + 15] = scan_fallbacks;
+            dbg[blockIdx.x * FZ_TRACE + 7] = scan_ncand;
+            dbg[blockIdx.x * FZ_TRACE + 4] = tr_issue;  // (overwrite covariance warps 4..6 slots)
+            dbg[blockIdx.x * FZ_TRACE + 5] = tr_full;
+            dbg[blockIdx.x * FZ_TRACE + 6] = tr_comp;
             unsigned long long g_end;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
-            dbg[blockIdx.x * 16 + 3] = (long long)(g_end - g_start);   // ns, this CTA's lifetime (overwrites covariance warp 3's slot)
-            dbg[blockIdx.x * 16 + 2] = (long long)g_start;             // ns, absolute start (overwrites covariance warp 2's slot)
+            dbg[blockIdx.x * FZ_TRACE + 3] = (long long)(g_end - g_start);   // ns, this CTA's lifetime (overwrites covariance warp 3's slot)
+            dbg[blockIdx.x * FZ_TRACE + 2] = (long long)g_start;             // ns, absolute start (overwrites covariance warp 2's slot)
         }
+        fused_drain_worker(fz_smem, soa, K, out);
     }
     // The last CTA to finish re-arms the ticket counter for the next launch (launches of one handle are
     // serialised by the host, and by now every covariance warp has drawn a ticket >= W).
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (dbg) {
+            dbg[blockIdx.x * FZ_TRACE + 17] = ctl->drained_windows;
+            dbg[blockIdx.x * FZ_TRACE + 18] = clock64() - t_start;  // every window of this CTA is finished
+        }
+        if (out.npeer > 0) __threadfence_system(); else __threadfence();
         if (atomicAdd(&work_ctr[1], 1u) == gridDim.x - 1) {
             work_ctr[0] = 0;
             work_ctr[1] = 0;
             __threadfence();
+            // every CTA's peak bins (fenced at system scope above) are on their way to the peers: raise this GPU's
+            // epoch flag in every peer's flag array - the consumer side of the fused all-gather waits on these
+            if (out.npeer > 0 && gather_flags.epoch) {
+                __threadfence_system();
+                for (int p = 0; p < out.npeer; ++p)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gather_flags.peer[p] + out.rank), "r"(gather_flags.epoch) : "memory");
+            }
         }
     }
 }

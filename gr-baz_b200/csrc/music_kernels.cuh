@@ -731,25 +731,14 @@ __global__ void __launch_bounds__(128) eig_kernel(const double *__restrict__ R, 
 // ------------------------------------------------------------------------------------------
 constexpr int EIGC_WARPS = 4;
 
+// One warp, one window: A (M x M complex, row-major, shared memory) holds R on entry and the rotated matrix (its diagonal =
+// the eigenvalues) on exit, V (M x M scratch) the eigenvectors as columns; rot / pair: M/2 entries of warp-private scratch.
 template <int M>
-__global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double *__restrict__ R, double *__restrict__ evals,
-                                                                   double *__restrict__ Vt, int W)
+__device__ __forceinline__ void eig_coop_warp(double2 *A, double2 *V, double (*rot)[4], int (*pair)[2], const int lane)
 {
     static_assert(M % 2 == 0 && M <= MAXM, "even M only");
     constexpr int H = M / 2;
-    __shared__ double2 sA[EIGC_WARPS][M * M];
-    __shared__ double2 sV[EIGC_WARPS][M * M];
-    __shared__ double sRot[EIGC_WARPS][H][4];  // c, Re(s w), Im(s w), unused
-    __shared__ int sPair[EIGC_WARPS][H][2];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * EIGC_WARPS + warp;
-    if (w >= W) return;
-    double2 *A = sA[warp], *V = sV[warp];
-    const double2 *Rw = reinterpret_cast<const double2 *>(R) + (size_t)w * M * M;
-    for (int i = lane; i < M * M; i += 32) {
-        A[i] = Rw[i];
-        V[i] = make_double2((i / M == i % M) ? 1.0 : 0.0, 0.0);
-    }
+    for (int i = lane; i < M * M; i += 32) V[i] = make_double2((i / M == i % M) ? 1.0 : 0.0, 0.0);
     __syncwarp();
     double prev_off = 1e300;
     for (int sweep = 0; sweep < 60; ++sweep) {
@@ -786,18 +775,18 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
                 if (gg != gg) t = gg;  // NaN input stays NaN
                 const double c = rsqrt(fma(t, t, 1.0));
                 const double sn = t * c;
-                sRot[warp][lane][0] = c;
-                sRot[warp][lane][1] = sn * g2.x * rg;
-                sRot[warp][lane][2] = sn * g2.y * rg;
-                sPair[warp][lane][0] = p;
-                sPair[warp][lane][1] = q;
+                rot[lane][0] = c;
+                rot[lane][1] = sn * g2.x * rg;
+                rot[lane][2] = sn * g2.y * rg;
+                pair[lane][0] = p;
+                pair[lane][1] = q;
             }
             __syncwarp();
             // columns: B[k][p] = c A[k][p] - conj(sw) A[k][q],  B[k][q] = sw A[k][p] + c A[k][q]   (A and V)
             for (int it = lane; it < M * H; it += 32) {
                 const int k = it / H, i = it % H;
-                const int p = sPair[warp][i][0], q = sPair[warp][i][1];
-                const double c = sRot[warp][i][0], swr = sRot[warp][i][1], swi = sRot[warp][i][2];
+                const int p = pair[i][0], q = pair[i][1];
+                const double c = rot[i][0], swr = rot[i][1], swi = rot[i][2];
                 {
                     const double2 ap = A[k * M + p], aq = A[k * M + q];
                     A[k * M + p] = make_double2(c * ap.x - (swr * aq.x + swi * aq.y), c * ap.y - (swr * aq.y - swi * aq.x));
@@ -814,15 +803,15 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
             // (k fastest across lanes: a row is contiguous, so the accesses are bank-conflict free)
             for (int it = lane; it < M * H; it += 32) {
                 const int i = it / M, k = it % M;
-                const int p = sPair[warp][i][0], q = sPair[warp][i][1];
-                const double c = sRot[warp][i][0], swr = sRot[warp][i][1], swi = sRot[warp][i][2];
+                const int p = pair[i][0], q = pair[i][1];
+                const double c = rot[i][0], swr = rot[i][1], swi = rot[i][2];
                 const double2 bp = A[p * M + k], bq = A[q * M + k];
                 A[p * M + k] = make_double2(c * bp.x - (swr * bq.x - swi * bq.y), c * bp.y - (swr * bq.y + swi * bq.x));
                 A[q * M + k] = make_double2(c * bq.x + (swr * bp.x + swi * bp.y), c * bq.y + (swr * bp.y - swi * bp.x));
             }
             __syncwarp();
             if (lane < H) {  // exact zeros / real diagonal where the rotation says so
-                const int p = sPair[warp][lane][0], q = sPair[warp][lane][1];
+                const int p = pair[lane][0], q = pair[lane][1];
                 A[p * M + q] = make_double2(0.0, 0.0);
                 A[q * M + p] = make_double2(0.0, 0.0);
                 A[p * M + p].y = 0.0;
@@ -831,9 +820,13 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
             __syncwarp();
         }
     }
-    // ascending, stable ranks; eigenvector j -> slot rank(j), phase fixed so that component 0 is real
-    double *ew = evals + (size_t)w * M;
-    double2 *vw = reinterpret_cast<double2 *>(Vt) + (size_t)w * M * M;
+}
+
+// ascending, stable ranks; eigenvector j -> vw[rank(j)][.] (component i), phase fixed so that component 0 is real;
+// ew (may be null): the eigenvalues in the same order
+template <int M>
+__device__ __forceinline__ void eig_coop_store(const double2 *A, const double2 *V, double *ew, double2 *vw, const int lane)
+{
     for (int it = lane; it < M * M; it += 32) {
         const int j = it / M, i = it % M;  // column j, component i
         const double wj = A[j * M + j].x;
@@ -843,8 +836,27 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
         eig_phase(V[0 * M + j].x, V[0 * M + j].y, pr, pi);
         const double2 v = V[i * M + j];
         vw[rank * M + i] = make_double2(v.x * pr - v.y * pi, i == 0 ? 0.0 : v.x * pi + v.y * pr);
-        if (i == 0) ew[rank] = wj;
+        if (i == 0 && ew) ew[rank] = wj;
     }
+}
+
+template <int M>
+__global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double *__restrict__ R, double *__restrict__ evals,
+                                                                   double *__restrict__ Vt, int W)
+{
+    constexpr int H = M / 2;
+    __shared__ double2 sA[EIGC_WARPS][M * M];
+    __shared__ double2 sV[EIGC_WARPS][M * M];
+    __shared__ double sRot[EIGC_WARPS][H][4];  // c, Re(s w), Im(s w), unused
+    __shared__ int sPair[EIGC_WARPS][H][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * EIGC_WARPS + warp;
+    if (w >= W) return;
+    double2 *A = sA[warp], *V = sV[warp];
+    const double2 *Rw = reinterpret_cast<const double2 *>(R) + (size_t)w * M * M;
+    for (int i = lane; i < M * M; i += 32) A[i] = Rw[i];
+    eig_coop_warp<M>(A, V, sRot[warp], sPair[warp], lane);
+    eig_coop_store<M>(A, V, evals + (size_t)w * M, reinterpret_cast<double2 *>(Vt) + (size_t)w * M * M, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -881,11 +893,34 @@ __global__ void prep_table_kernel(const float2 *__restrict__ tab, double *__rest
 //
 //   ARGMAX: n == 1 fused peak pick, ordered (P desc, bin asc), P > 0 strictly, NaN never.
 // ------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 8;  // GPUs of one NVSwitch domain
 struct PeakOut {
     float *angles;   // [W][n]
     float *levels;   // [W][n] or null
     int32_t *bins;   // [W][n] or null
+    // Fused all-gather of the peak bins: with npeer = G > 0 this GPU holds the windows
+    // w = i * G + rank of a round-robin sharded stream (i = local window index) and every kernel that writes a
+    // peak bin also stores it at stream position w of EVERY peer's gather buffer (peer-mapped device memory, NVLink
+    // stores straight from the scan epilogue; peer[rank] is this GPU's own buffer) - no collective kernel runs.
+    int32_t *peer[MAX_PEERS];
+    int npeer, rank, n;
 };
+
+struct GatherFlags {
+    unsigned *peer[MAX_PEERS];  // peer[p][r] = last epoch in which GPU r finished writing its bins into GPU p's buffer
+    unsigned epoch;             // 0: no signalling
+};
+
+// peak bin of local output slot o (= local window * n + r)
+__device__ __forceinline__ void peak_store_bin(const PeakOut &out, const size_t o, const int kk)
+{
+    if (out.bins) out.bins[o] = kk;
+    if (out.npeer > 0) {
+        const size_t w = o / (size_t)out.n, r = o - w * (size_t)out.n;
+        const size_t go = (w * (size_t)out.npeer + (size_t)out.rank) * (size_t)out.n + r;
+        for (int p = 0; p < out.npeer; ++p) out.peer[p][go] = kk;
+    }
+}
 
 __device__ __forceinline__ bool peak_better(double Pa, int ka, double Pb, int kb)
 {
@@ -1024,7 +1059,7 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const double *__restrict__ s
                 out.angles[o] = 0.f;                                      // (0,0) initial pair, :95
                 if (out.levels) out.levels[o] = 0.f;
             }
-            if (out.bins) out.bins[o] = kk;
+            peak_store_bin(out, o, kk);
         }
     }
 }
@@ -1237,7 +1272,7 @@ __global__ void __launch_bounds__(TILE, 3) scan_peak1_kernel(const double *__res
             out.angles[o] = 0.f;                                      // (0,0) initial pair, :95
             if (out.levels) out.levels[o] = 0.f;
         }
-        if (out.bins) out.bins[o] = kk;
+        peak_store_bin(out, o, kk);
     }
 }
 
@@ -1278,7 +1313,7 @@ __global__ void __launch_bounds__(256) topn_kernel(const double *__restrict__ P6
                 out.angles[o] = 0.f;
                 if (out.levels) out.levels[o] = 0.f;
             }
-            if (out.bins) out.bins[o] = bk;
+            peak_store_bin(out, o, bk);
         }
         first = false;
         prevP = bP;
@@ -1336,7 +1371,7 @@ __global__ void __launch_bounds__(256) topn_local_kernel(const double *__restric
                 out.angles[o] = 0.f;
                 if (out.levels) out.levels[o] = 0.f;
             }
-            if (out.bins) out.bins[o] = bk;
+            peak_store_bin(out, o, bk);
         }
         __syncwarp();
     }

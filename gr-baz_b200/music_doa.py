@@ -37,15 +37,23 @@ def _table_c64(array_response, resolution, m):
 
 
 class music_doa(object):
-    def __init__(self, m, n, nsamples, array_response, resolution, device=0):
+    def __init__(self, m, n, nsamples, array_response, resolution, device=0, devices=None):
+        """``devices`` (extension): a list of CUDA device ordinals - the block then owns one engine per GPU and
+        ``work()`` deals its windows round-robin to them (``music_b200_create_multi``); the C++ block reads the same
+        list from the environment variable BAZ_MUSIC_DOA_DEVICES so that flowgraph parameters do not change."""
         self._lib = _capi.load()
         self._h = ctypes.c_void_p()
         self.m, self.n, self.nsamples, self.resolution = int(m), int(n), int(nsamples), int(resolution)
         if self.m <= 0 or self.resolution <= 0:
             raise ValueError("m and resolution must be > 0")
         table = _table_c64(array_response, self.resolution, self.m)
-        rc = self._lib.music_b200_create(ctypes.byref(self._h), self.m, self.n, self.nsamples, self.resolution,
-                                         table.ctypes.data, int(device))
+        if devices is not None:
+            devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.music_b200_create_multi(ctypes.byref(self._h), self.m, self.n, self.nsamples, self.resolution,
+                                                   table.ctypes.data, devs, len(devices))
+        else:
+            rc = self._lib.music_b200_create(ctypes.byref(self._h), self.m, self.n, self.nsamples, self.resolution,
+                                             table.ctypes.data, int(device))
         if rc == _capi.EINVAL:
             raise ValueError(self._lib.music_b200_last_error(None).decode())
         _capi.check(rc)
@@ -213,6 +221,45 @@ class music_doa(object):
         rc = self._lib.music_b200_process_planar_device(self._h, ptrs, int(hop), int(nwindows), d_angles, d_levels, d_spectrum, d_bins, stream)
         _capi.check(rc, self._h)
 
+    # -- extension: sharded device entry / fused all-gather of the peak bins ------------
+    def device_count(self):
+        return int(self._lib.music_b200_device_count(self._h))
+
+    def process_device_sharded(self, d_in, nwindows_total, d_angles, d_levels=None, d_bins_all=None, streams=None):
+        """Multi-device handle, inputs resident: ``d_in[g]`` / ``d_angles[g]`` / ``d_levels[g]`` are device addresses
+        (ints) on device g holding the shard w = i*G + g; ``d_bins_all[p]`` is an int32 [nwindows_total][n] array on
+        device p that receives EVERY shard's peak bins in stream order (stored by the scan epilogues over NVLink)."""
+        G = self.device_count()
+        arr = lambda v: None if v is None else (ctypes.c_void_p * G)(*[None if x is None else int(x) for x in v])
+        a_in, a_ang, a_lvl, a_bins, a_st = arr(d_in), arr(d_angles), arr(d_levels), arr(d_bins_all), arr(streams)
+        _capi.check(self._lib.music_b200_process_device_sharded(self._h, a_in, int(nwindows_total), a_ang, a_lvl, a_bins, a_st), self._h)
+
+    def gather_create(self, total_windows):
+        """One rank per process: allocate this rank's stream-ordered gather buffer; returns the 128 bytes of CUDA IPC
+        handles to exchange with the other ranks (see include/music_b200.h)."""
+        buf = (ctypes.c_ubyte * 128)()
+        _capi.check(self._lib.music_b200_gather_create(self._h, int(total_windows), buf), self._h)
+        return bytes(buf)
+
+    def gather_attach(self, nranks, rank, all_handles):
+        raw = b"".join(all_handles)
+        if len(raw) != 128 * int(nranks):
+            raise ValueError("need 128 bytes of IPC handles per rank")
+        buf = (ctypes.c_ubyte * len(raw)).from_buffer_copy(raw)
+        _capi.check(self._lib.music_b200_gather_attach(self._h, int(nranks), int(rank), buf), self._h)
+
+    def gather_wait(self, stream=None):
+        _capi.check(self._lib.music_b200_gather_wait(self._h, stream), self._h)
+
+    def gather_read(self, total_windows):
+        """Host copy (int32 (total_windows, n), stream order) of this rank's gather buffer."""
+        out = np.empty((int(total_windows), self.n), np.int32)
+        _capi.check(self._lib.music_b200_gather_read(self._h, out.ctypes.data, out.size), self._h)
+        return out
+
+    def gather_buffer_ptr(self):
+        return int(self._lib.music_b200_gather_buffer(self._h) or 0)
+
     def set_stage_timing(self, enable):
         _capi.check(self._lib.music_b200_set_stage_timing(self._h, 1 if enable else 0), self._h)
 
@@ -222,6 +269,12 @@ class music_doa(object):
         ch = ctypes.c_uint64(0)
         _capi.check(self._lib.music_b200_get_stage_times(self._h, ms, ctypes.byref(ch)), self._h)
         return list(ms), int(ch.value)
+
+    def fused8_stats(self):
+        """(windows solved by squaring, windows solved by the Jacobi fallback) of the fused M = 8 kernel so far."""
+        v = (ctypes.c_uint64 * 2)()
+        _capi.check(self._lib.music_b200_debug_fused8_stats(self._h, v), self._h)
+        return int(v[0]), int(v[1])
 
     def launch_count(self):
         return int(self._lib.music_b200_launch_count(self._h))

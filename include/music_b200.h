@@ -42,7 +42,7 @@ extern "C" {
 typedef struct music_b200 music_b200;
 
 /* ABI version of this header (bumped on any signature change). */
-int music_b200_version(void);
+int music_b200_version(void);  /* 2: multi-device handles, fused bins all-gather */
 
 /*
  * Replaces baz_make_music_doa() + the constructor
@@ -54,6 +54,52 @@ int music_b200_version(void);
  */
 int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsamples,
                       uint32_t resolution, const float *table_c64, int device);
+
+/*
+ * The same block spread over `ndev` GPUs of one node (windows are independent, so they shard
+ * round-robin, window w -> devices[w mod ndev], and every device keeps a full copy of the array response).  The handle
+ * behaves like one from music_b200_create():
+ *   process_host()     deals the call's windows round-robin at WINDOW granularity to the devices (strided 2-D copies,
+ *                      one PCIe link per device, no interleaving pass on the host) and returns the outputs in stream
+ *                      order - one work() call of one flowgraph block uses every GPU and every PCIe link;
+ *   set_table() / set_geometry() / set_peak_mode()  apply to every device;
+ *   process_device()   goes to the device the input pointer lives on;  process_device_sharded() (below) runs all of them;
+ *   planar, reducer, stage-timing entries are served by devices[0].
+ * lib/baz_music_doa.cc picks the devices from the environment variable BAZ_MUSIC_DOA_DEVICES ("0,1,2,3" or "all").
+ */
+int music_b200_create_multi(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsamples, uint32_t resolution,
+                            const float *table_c64, const int *devices, int ndev);
+int music_b200_device_count(const music_b200 *h);
+
+/*
+ * Device-resident, sharded form of work() on a multi-device handle: device g (= devices[g] of create_multi) holds in
+ * d_in_c64[g] the windows w = i * G + g of a stream of nwindows_total windows (i = local index, compacted) and receives
+ * their angles / levels in d_angles[g] / d_levels[g] ([ceil((nwindows_total - g) / G)][n], levels may be NULL).
+ * d_bins_all (may be NULL): G device arrays, d_bins_all[p] on device p, each int32 [nwindows_total][n] in STREAM order.
+ * The all-gather of the peak bins is fused into the scan epilogue: the kernel of shard g stores bin w into
+ * d_bins_all[p][w] for every p over NVLink (peer-mapped memory; no NCCL, no separate collective kernel), so when the
+ * G streams have finished every device holds all peaks.  streams (may be NULL): one cudaStream_t per device.
+ */
+int music_b200_process_device_sharded(music_b200 *h, const float *const *d_in_c64, uint32_t nwindows_total, float *const *d_angles,
+                                      float *const *d_levels, int32_t *const *d_bins_all, void *const *streams);
+
+/*
+ * The same fused all-gather when every GPU belongs to its own PROCESS (one rank per GPU, e.g. under torchrun): each rank
+ *   1. gather_create(h, total_windows, handles)  allocates its stream-ordered gather buffer (int32 [total_windows][n]) and
+ *      epoch flags and returns their two 64-byte CUDA IPC handles;
+ *   2. exchanges the handles with the other ranks by any means (bench.py: one all_gather of 128 bytes at start-up);
+ *   3. gather_attach(h, nranks, rank, all_handles)  maps the peers' buffers.
+ * From then on every process_device() call of this handle treats its nwindows windows as the shard w = i * nranks + rank
+ * and its scan epilogue stores the peak bins into every rank's gather buffer; the last CTA raises this rank's epoch flag
+ * at every peer.  gather_wait(h, stream) enqueues a one-warp kernel that returns when all ranks' flags have reached this
+ * rank's call count, i.e. when gather_buffer(h) holds every rank's bins of the latest call (all ranks must make the same
+ * sequence of calls, as with any collective).  ncclAllGather stays the reference implementation the tests compare with.
+ */
+int music_b200_gather_create(music_b200 *h, uint32_t total_windows, unsigned char *ipc_handles /* [2][64] */);
+int music_b200_gather_attach(music_b200 *h, int nranks, int rank, const unsigned char *all_handles /* [nranks][2][64] */);
+int music_b200_gather_wait(music_b200 *h, void *stream);
+const int32_t *music_b200_gather_buffer(const music_b200 *h);
+int music_b200_gather_read(music_b200 *h, int32_t *host_out, uint32_t count); /* synchronous copy of the first `count` entries */
 
 /*
  * Replaces baz_music_doa::set_array_response() (/root/reference/lib/baz_music_doa.cc:60-70).
@@ -142,6 +188,9 @@ int music_b200_get_table(music_b200 *h, float *table_c64);
  * hands to work(): input_items[0], output_items[0..2]).  Host<->device copies are done
  * inside (chunked, double-buffered).  levels / spectrum / bins may be NULL, mirroring
  * output_items.size() (:97-99, :148-149); NULL skips that work.
+ * Pageable caller memory (GNU Radio's circular buffers, numpy arrays) of 1 MiB or more is pinned with cudaHostRegister
+ * the first time it is seen and remembered in the handle (up to 16 ranges; released by destroy()), so that later calls
+ * on the same buffers copy at the pinned rate; MUSIC_B200_HOSTREG=0 in the environment turns that off.
  */
 int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindows,
                             float *angles, float *levels, float *spectrum, int32_t *bins);
@@ -184,6 +233,10 @@ int music_b200_get_stage_times(music_b200 *h, double *ms4, uint64_t *chunks);
 /* Debug: copy the fused kernel's per-CTA clock64 trace (16 int64 per CTA; only when the handle
  * was created with MUSIC_B200_TRACE=1 in the environment). */
 int music_b200_debug_fused_trace(music_b200 *h, long long *host_out, int max_ctas);
+
+/* Debug: cumulative window counts of the fused M = 8 kernel - out2[0] solved by the principal-eigenvector (squaring) solver,
+ * out2[1] by the Jacobi fallback. */
+int music_b200_debug_fused8_stats(music_b200 *h, uint64_t *out2);
 
 /* Last error text for this handle; h == NULL returns the last create() failure. */
 const char *music_b200_last_error(const music_b200 *h);

@@ -32,6 +32,7 @@
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 baz_music_doa_sptr baz_make_music_doa(unsigned int m, unsigned int n, unsigned int nsamples,
                                       const array_response_t &array_response, unsigned int resolution)
@@ -45,6 +46,25 @@ static int device_from_env()
     return e ? atoi(e) : 0;
 }
 
+/* BAZ_MUSIC_DOA_DEVICES="0,1,2,3": one engine per listed GPU behind this ONE block - work() deals its windows
+   round-robin to them (music_b200_create_multi), so an unchanged flowgraph uses every GPU and every PCIe link of the
+   node.  Unset: the single device of BAZ_MUSIC_DOA_DEVICE. */
+static std::vector<int> devices_from_env()
+{
+    std::vector<int> d;
+    const char *e = getenv("BAZ_MUSIC_DOA_DEVICES");
+    if (!e) return d;
+    for (const char *p = e; *p;) {
+        char *end = NULL;
+        const long v = strtol(p, &end, 10);
+        if (end == p) break;
+        d.push_back((int)v);
+        p = end;
+        while (*p == ',' || *p == ' ') ++p;
+    }
+    return d;
+}
+
 baz_music_doa::baz_music_doa(unsigned int m, unsigned int n, unsigned int nsamples,
                              const array_response_t &array_response, unsigned int resolution)
     : gr::sync_block("music_doa", gr::io_signature::make(1, 1, nsamples * sizeof(gr_complex)),
@@ -53,7 +73,9 @@ baz_music_doa::baz_music_doa(unsigned int m, unsigned int n, unsigned int nsampl
 {
     if (array_response.size() != resolution) throw std::invalid_argument("music_doa: array_response.size() != resolution");
     const std::vector<float> table = flatten(array_response);
-    const int rc = music_b200_create(&d_handle, m, n, nsamples, resolution, table.data(), device_from_env());
+    const std::vector<int> devices = devices_from_env();
+    const int rc = devices.empty() ? music_b200_create(&d_handle, m, n, nsamples, resolution, table.data(), device_from_env())
+                                   : music_b200_create_multi(&d_handle, m, n, nsamples, resolution, table.data(), devices.data(), (int)devices.size());
     if (rc == MUSIC_B200_EINVAL) throw std::invalid_argument(std::string("music_doa: ") + music_b200_last_error(NULL));
     if (rc != MUSIC_B200_OK) throw std::runtime_error(std::string("music_doa: ") + music_b200_last_error(NULL));
 

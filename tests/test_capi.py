@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(_capi.lib_path())
     for sym in declared:
         assert getattr(raw, sym) is not None
-    assert lib.music_b200_version() == 1
+    assert lib.music_b200_version() == 2
 
 
 def test_create_rejects_bad_parameters(lib):

@@ -34,9 +34,18 @@ def test_block_builds_and_exports_reference_factory(built):
 
 
 @pytest.mark.gpu
-def test_block_work_matches_oracle(built, tmp_path):
+@pytest.mark.parametrize("devices", [None, "0", "all"])
+def test_block_work_matches_oracle(built, tmp_path, devices):
+    """devices: BAZ_MUSIC_DOA_DEVICES of the block's environment - None = the single-device handle, "0" = a
+    multi-device handle over one GPU, "all" = every GPU of the box (windows dealt round-robin; same outputs)."""
+    import torch
+    env = dict(os.environ)
+    if devices == "all":
+        devices = ",".join(str(i) for i in range(torch.cuda.device_count()))
+    if devices is not None:
+        env["BAZ_MUSIC_DOA_DEVICES"] = devices
     cfg = synth.config(1)
-    W = 12
+    W = 13
     t1 = helpers.table_for(cfg)
     cfg2 = synth.config(1, geometry="ula_y")
     t2 = helpers.table_for(cfg2)
@@ -47,7 +56,7 @@ def test_block_work_matches_oracle(built, tmp_path):
         f.write(t1.view(np.float32).tobytes())
         f.write(t2.view(np.float32).tobytes())
         f.write(x.view(np.float32).tobytes())
-    r = subprocess.run([os.path.join(built, "test_block"), str(fin), str(fout)], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(built, "test_block"), str(fin), str(fout)], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     assert "MUSIC DOA: M: 4, N: 1, # samples: 4096, angular resolution: 360" in r.stderr  # banner, reference :52
     assert "Updating array response" in r.stderr  # reference :65

@@ -24,7 +24,7 @@ b = torch.empty((W, 1), dtype=torch.int32, device=dev)
 for _ in range(3):
     blk.process_device(d_in.data_ptr(), W, a.data_ptr(), l.data_ptr(), None, b.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
-tr = np.zeros((148, 16), np.int64)
+tr = np.zeros((148, 32), np.int64)
 blk._lib.music_b200_debug_fused_trace(blk._h, tr.ctypes.data, 148)
 cov_end = tr[:, 0]
 print("cycles (mean over CTAs):")
@@ -35,3 +35,5 @@ print("  scan: exact-evaluation phase %9.0f cycles, candidates/CTA %7.1f, full-f
 print("  scan thread 0 inside the sweeps: issue+slot-wait %9.0f, tile-arrival wait %9.0f, loads+MMA+post %9.0f" % (tr[:, 4].mean(), tr[:, 5].mean(), tr[:, 6].mean()))
 print("  CTA lifetime by %%globaltimer: %.1f us mean -> SM clock %.0f MHz; CTA start skew %.1f us; first start to last end %.1f us" % (tr[:, 3].mean() / 1e3, (tr[:, 11] / (tr[:, 3] / 1e3)).mean(), (tr[:, 2].max() - tr[:, 2].min()) / 1e3, ((tr[:, 2] + tr[:, 3]).max() - tr[:, 2].min()) / 1e3))
 print("  tail after last cov  %9.0f   (eig warp exit - last cov %9.0f, scan exit - eig exit %9.0f)" % ((tr[:, 11] - cov_end).mean(), (tr[:, 8] - cov_end).mean(), (tr[:, 11] - tr[:, 8]).mean()))
+print("  tensor-core passes ended %9.0f, windows taken by the fp64 drain workers %5.1f / CTA, Jacobi rounds %5.2f / CTA" % (tr[:, 16].mean(), tr[:, 17].mean(), tr[:, 19].mean()))
+print("  CTA done (all outputs written) %9.0f mean, %9.0f max; after the last covariance warp: %9.0f mean" % (tr[:, 18].mean(), tr[:, 18].max(), (tr[:, 18] - cov_end).mean()))
