@@ -76,7 +76,10 @@ struct music_b200 {
     cudaStream_t s_cov = nullptr, s_scan = nullptr;
     cudaEvent_t ev_in = nullptr;
     bool pipeline = false;   // MUSIC_B200_PIPE=1 enables the sub-batch pipeline (launch-bound at 10k windows: off)
-    unsigned *work_ctr = nullptr;      // fused kernel: [0] window tickets, [1] finished CTAs (self-resetting)
+    unsigned *work_ctr = nullptr;      // persistent kernels: ring of self-resetting (window tickets, finished CTAs) pairs, CTR_RING per slot
+    unsigned ctr_seq[2] = {0, 0};      // next ring entry per slot
+    unsigned idle_ns = 100;            // fused kernel: sleep of an idle drain worker (MUSIC_B200_IDLE_NS)
+    bool pdl = true;                   // fused M = 4 kernel: programmatic dependent launch (MUSIC_B200_PDL=0 turns it off)
     cudaEvent_t fused_done = nullptr;  // orders persistent launches that share a ticket counter but not a stream
     bool fused_used[2] = {false, false};
     int eig_mode = 0;                 // fused kernel: 0 principal eigenvector by squaring (default), 1 / 2 Jacobi with four lanes / one lane per window (MUSIC_B200_EIG=jacobi|jacobi1)
@@ -259,6 +262,7 @@ EncodeTiledFn encode_tiled_fn()
         }                                                                                        \
     }
 
+constexpr unsigned CTR_RING = 256;  // ticket-counter pairs per slot (see ticket_counter)
 constexpr int NSLOT = 3;           // workspace ring for the cov -> eig/scan software pipeline
 constexpr uint32_t MIN_SUB = 1024; // windows; below 2*MIN_SUB a call is not split
 
@@ -343,7 +347,12 @@ unsigned *ticket_counter(music_b200 *h, int slot, cudaStream_t st)
     }
     h->fused_used[slot] = true;
     h->last_fused_stream[slot] = st;
-    return h->work_ctr + 2 * slot;
+    // Every launch draws its own pair from the slot's ring: with programmatic dependent launch the CTAs of launch k + 1
+    // start on the SMs launch k has left while k's last CTAs are still running, so the two must not share tickets.  A
+    // pair is reused CTR_RING launches later; launches on one stream overlap only with their neighbours, and each
+    // persistent CTA owns a whole SM, so fewer than CTR_RING launches are ever resident together.
+    const unsigned e = h->ctr_seq[slot]++ % CTR_RING;
+    return h->work_ctr + 2 * ((size_t)slot * CTR_RING + e);
 }
 
 // K1: covariance of W windows into ws.R, on `st`.
@@ -547,14 +556,31 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         const DeviceTable &tb = h->table[h->cur_table];
         const PeakOut po = make_peak_out(h, d_ang, d_lvl, d_bins, 0);
         const GatherFlags gf = make_gather_flags(h, true);
-        if (planar)
-            music4_fused_kernel<true><<<grid, FZ_THREADS, FZ_SMEM, st>>>(nullptr, *planar, 0ull, hop, tb.fz, tb.c64, tb.na_max, (int)nwindows,
-                                                                         (int)h->N, (int)h->K, po, ctr, h->fused_trace, h->eig_mode,
-                                                                         tb.soa, gf, h->mma_fin_max);
-        else
-            music4_fused_kernel<false><<<grid, FZ_THREADS, FZ_SMEM, st>>>(d_in, PlanarStreams{}, 0ull, 0u, tb.fz, tb.c64, tb.na_max,
-                                                                          (int)nwindows, (int)h->N, (int)h->K, po, ctr, h->fused_trace,
-                                                                          h->eig_mode, tb.soa, gf, h->mma_fin_max);
+        // Programmatic dependent launch: when the previous operation on `st` is another launch of this kernel, the new
+        // CTAs are placed as soon as the old ones leave their SMs (every CTA signals launch_dependents at its start) instead
+        // of after the whole grid has drained; the kernel orders its own output writes behind the previous grid with
+        // griddepcontrol.wait.  After any other kind of operation the launch is an ordinary stream-ordered one.
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(FZ_THREADS); lc.dynamicSmemBytes = FZ_SMEM; lc.stream = st;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        la[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = la; lc.numAttrs = h->pdl ? 1 : 0;
+        const int W_i = (int)nwindows, N_i = (int)h->N, K_i = (int)h->K;
+        const bool tr = h->fused_trace != nullptr;  // MUSIC_B200_TRACE=1: the instantiation with the clock64 trace
+        const unsigned char *fz = tb.fz;
+        const float *c64 = tb.c64, *na_max = tb.na_max;
+        cudaError_t le;
+        if (planar) {
+            auto kern = tr ? music4_fused_kernel<true, true> : music4_fused_kernel<true, false>;
+            le = cudaLaunchKernelEx(&lc, kern, (const float *)nullptr, *planar, 0ull, (unsigned)hop, fz, c64, na_max, W_i, N_i, K_i, po, ctr,
+                                    h->fused_trace, h->eig_mode, gf, h->mma_fin_max, h->idle_ns);
+        } else {
+            auto kern = tr ? music4_fused_kernel<false, true> : music4_fused_kernel<false, false>;
+            le = cudaLaunchKernelEx(&lc, kern, d_in, PlanarStreams{}, 0ull, 0u, fz, c64, na_max, W_i, N_i, K_i, po, ctr, h->fused_trace,
+                                    h->eig_mode, gf, h->mma_fin_max, h->idle_ns);
+        }
+        CU(h, le);
         h->launches++;
         if (tev) for (int i = 1; i < 5; ++i) cudaEventRecord(tev[i], st);
         CU(h, cudaGetLastError());
@@ -901,6 +927,8 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         if (const char *e = getenv("MUSIC_B200_FUSED")) h->fused = atoi(e) != 0;
         if (const char *e = getenv("MUSIC_B200_COVN")) h->covn = atoi(e) != 0;
         if (const char *e = getenv("MUSIC_B200_EIG")) h->eig_mode = !strcmp(e, "jacobi") ? 1 : !strcmp(e, "jacobi1") ? 2 : 0;
+        if (const char *e = getenv("MUSIC_B200_PDL")) h->pdl = atoi(e) != 0;
+        if (const char *e = getenv("MUSIC_B200_IDLE_NS")) h->idle_ns = (unsigned)std::max(0, atoi(e));
         if (const char *e = getenv("MUSIC_B200_MMA_FIN")) h->mma_fin_max = std::max(-1, std::min(8, atoi(e)));
         CU(h, cudaFuncSetAttribute(covN_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
         CU(h, cudaFuncSetAttribute(covN_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CN_SMEM));
@@ -908,15 +936,17 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         CU(h, cudaMalloc(&h->f8_stats, 2 * sizeof(unsigned)));
         CU(h, cudaMemset(h->f8_stats, 0, 2 * sizeof(unsigned)));
         CU(h, cudaEventCreateWithFlags(&h->fused_done, cudaEventDisableTiming));
-        CU(h, cudaMalloc(&h->work_ctr, 4 * sizeof(unsigned)));  // two self-resetting (tickets, finished CTAs) pairs
-        CU(h, cudaMemset(h->work_ctr, 0, 4 * sizeof(unsigned)));
+        CU(h, cudaMalloc(&h->work_ctr, 2 * CTR_RING * 2 * sizeof(unsigned)));  // self-resetting (tickets, finished CTAs) pairs
+        CU(h, cudaMemset(h->work_ctr, 0, 2 * CTR_RING * 2 * sizeof(unsigned)));
         if (const char *e = getenv("MUSIC_B200_HOSTREG")) h->hostreg = atoi(e) != 0;
         if (getenv("MUSIC_B200_TRACE")) {
             CU(h, cudaMalloc(&h->fused_trace, FZ_TRACE * sizeof(long long) * 1024));
             CU(h, cudaMemset(h->fused_trace, 0, FZ_TRACE * sizeof(long long) * 1024));
         }
-        CU(h, cudaFuncSetAttribute(music4_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
-        CU(h, cudaFuncSetAttribute(music4_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
+        CU(h, cudaFuncSetAttribute(music4_fused_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
+        CU(h, cudaFuncSetAttribute(music4_fused_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
+        CU(h, cudaFuncSetAttribute(music4_fused_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
+        CU(h, cudaFuncSetAttribute(music4_fused_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 6 * COV_CHUNK));
         CU(h, cudaFuncSetAttribute(cov4_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + COV_WARPS * 4 * COV_CHUNK));
         return upload_table(h, 0, table_c64, h->streams[0]);

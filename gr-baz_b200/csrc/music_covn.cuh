@@ -149,12 +149,13 @@ covN_tma_kernel(const __grid_constant__ CUtensorMap tm, double *__restrict__ R, 
         wring[wr & 7] = iw;
         ++wr;
     };
+    const uint64_t pol_stream = l2_policy_evict_first();
     auto issue = [&]() {  // producer only; the slot must be free
         const int slot = (int)(issued % SG);
         mbar_expect_tx(full0 + 8 * slot, STAGE);
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                     ::"r"(ring0 + slot * STAGE), "l"(tm_addr), "r"(0), "r"(iq * (STAGE / 128)), "r"(iw), "r"(full0 + 8 * slot)
-                     : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                     ::"r"(ring0 + slot * STAGE), "l"(tm_addr), "r"(0), "r"(iq * (STAGE / 128)), "r"(iw), "r"(full0 + 8 * slot), "l"(pol_stream)
+                     : "memory");  // evict_first: the stream is read once and must not push the steering table out of L2
         ++issued;
         if (++iq == cpw) { iq = 0; claim(); }
     };

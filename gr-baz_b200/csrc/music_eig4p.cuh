@@ -71,8 +71,10 @@ __device__ __forceinline__ bool eig4_principal_coop(const double *Rw, double *vw
     int st = (active && okc) ? 0 : 3;
     for (int it = 0; it < EIGP_MAXSQ; ++it) {
         if (!__any_sync(FULL, st < 2)) break;
+        if (active) {  // (idle lane groups alias the last window's scratch: they must not store)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) S[j * 4 + c] = make_double2(ar[c], ai[c]);
+            for (int c = 0; c < 4; ++c) S[j * 4 + c] = make_double2(ar[c], ai[c]);
+        }
         __syncwarp();
         double nr[4], ni[4];
 #pragma unroll
@@ -111,8 +113,10 @@ __device__ __forceinline__ bool eig4_principal_coop(const double *Rw, double *vw
     if (d1 > dm) { dm = d1; js = 1; }
     if (d2 > dm) { dm = d2; js = 2; }
     if (d3 > dm) { dm = d3; js = 3; }
+    if (active) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) S[j * 4 + c] = make_double2(ar[c], ai[c]);
+        for (int c = 0; c < 4; ++c) S[j * 4 + c] = make_double2(ar[c], ai[c]);
+    }
     __syncwarp();
     double ur[4], ui[4];
 #pragma unroll
@@ -123,7 +127,7 @@ __device__ __forceinline__ bool eig4_principal_coop(const double *Rw, double *vw
     __syncwarp();
     // two power steps with the original (scaled) matrix, then one more product for the certificate
     double wr = 0.0, wi = 0.0, lam = 0.0;
-#pragma unroll
+#pragma unroll 1  // (one copy of the step: instruction footprint, see music_fused.cuh)
     for (int step = 0; step < 3; ++step) {
         wr = 0.0; wi = 0.0;
 #pragma unroll
@@ -143,7 +147,7 @@ __device__ __forceinline__ bool eig4_principal_coop(const double *Rw, double *vw
         }
         const double s2 = eigp_sum4(fma(wr, wr, wi * wi));
         const double inv = 1.0 / sqrt(s2);
-        S[j] = make_double2(wr * inv, wi * inv);
+        if (active) S[j] = make_double2(wr * inv, wi * inv);
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < 4; ++c) { ur[c] = S[c].x; ui[c] = S[c].y; }

@@ -42,6 +42,14 @@
 // fl32(||a||^2).  FZ_B = 2^-15 leaves > 3x margin over this (already pessimistic) bound; a CPU emulation of the
 // screen with truncating fp32 accumulation measures <= 5e-7 ||a||^2, 60x below FZ_B (tests/test_screen_bound.py).
 //
+// INSTRUCTION FOOTPRINT.  Sixteen warps in four roles share one SM's instruction caches (L0 ~6 KB per sub-partition,
+// L1.5 32 KB per SM; beyond that instructions come from the L2, which this kernel keeps saturated with the input stream).
+// The first version of this file inlined everything (211 KB of SASS): code that runs once per pass / per drain unit then
+// cost ~50 cycles per INSTRUCTION (a 500-instruction lane merge: 26 k cycles) while loop bodies ran at ~6.  Hence:
+// everything rare or once-per-unit is out of line and shared (fused_exact_d, fused_recip, the Jacobi fallback), the two
+// table sweeps of a pass are one loop body, merges are rolled loops, and the clock64 trace exists only in the TRACE
+// instantiation of the kernel.
+//
 // Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does per
 // window except the optional spectrum port).
 #pragma once
@@ -69,7 +77,7 @@ constexpr float FZ_B = 3.0517578125e-05f;  // 2^-15, see "Screen error bound"
 
 constexpr int FZ_TRACE = 32;    // int64 trace words per CTA (MUSIC_B200_TRACE=1)
 constexpr int FZ_DG = 4;         // windows per drain group (= scan_bin's windows per thread)
-constexpr int FZ_NCH = 8;        // bin chunks per drain group: (group, chunk) is the unit a drain worker (one warp) takes
+constexpr int FZ_NCH = 16;       // interleaved bin chunks per drain group: (group, chunk) is the unit a drain worker (one warp) takes
 constexpr int FZ_NGS = 4;        // drain groups in flight
 
 struct FusedCtl {               // shared-memory control block
@@ -84,6 +92,7 @@ struct FusedCtl {               // shared-memory control block
     volatile unsigned mma_off;  // no further tensor-core passes: the drain workers take what is left
     volatile int dg_open;       // drain group currently handing out chunks (-1: none)
     unsigned drained_windows;   // statistics (trace)
+    unsigned drain_groups;
 };
 struct DrainGroup {
     volatile unsigned gs;       // first queue sequence number of the group
@@ -183,12 +192,13 @@ __global__ void prep_table_tc_kernel(const float *__restrict__ tab, unsigned cha
     }
 }
 
-// Exact fp64 strength of bin k for the window whose eigenvectors sit at shared address `ev`:
-// the same formula (and the same ||a||^2 fma order) as the unfused kernels.
-__device__ __forceinline__ double fused_exact_P(const float *__restrict__ tab_c64, int k, uint32_t ev)
+// Exact fp64 denominator d_k = ||G^H a_k||^2 of bin k for the window whose eigenvectors sit at shared address `ev`:
+// the same formula (and the same ||a||^2 fma order) as the unfused kernels.  ONE out-of-line copy serves the exact phase
+// of the tensor-core passes, the flat-spectrum fallback and the cold path of the drain workers.
+__device__ __noinline__ double fused_exact_d(const float *__restrict__ tab_c64, const int k, const uint32_t ev, const uint64_t pol_keep)
 {
     const float4 *row = reinterpret_cast<const float4 *>(tab_c64 + (size_t)k * 8);
-    const float4 x0 = __ldg(row), x1 = __ldg(row + 1);
+    const float4 x0 = ldg_f32x4_hint(row, pol_keep), x1 = ldg_f32x4_hint(row + 1, pol_keep);
     double ar[4], ai[4];
     ar[0] = x0.x; ai[0] = x0.y; ar[1] = x0.z; ai[1] = x0.w;
     ar[2] = x1.x; ai[2] = x1.y; ar[3] = x1.z; ai[3] = x1.w;
@@ -197,7 +207,70 @@ __device__ __forceinline__ double fused_exact_P(const float *__restrict__ tab_c6
     for (int i = 0; i < 4; ++i) na = fma(ar[i], ar[i], fma(ai[i], ai[i], na));
     double d = complement_denominator<4>(ar, ai, na, ev + 16 * 3 * 4);
     if (d < COMPLEMENT_GUARD * na) d = direct_denominator<4>(ar, ai, ev);
-    return 1.0 / d;
+    return d;
+}
+__device__ __noinline__ double fused_recip(const double d) { return 1.0 / d; }
+// the reference's replacement rule "1/d > 1/best" (strict '>' on the strengths, :132) for a d already known to be < best
+__device__ __noinline__ bool fused_recip_greater(const double d, const double best)
+{
+    return d < best * 0.99999999999999911182 /* 1 - 2^-50 */ || 1.0 / d > 1.0 / best;
+}
+__device__ __forceinline__ double fused_exact_P(const float *__restrict__ tab_c64, const int k, const uint32_t ev, const uint64_t pol_keep)
+{
+    return fused_recip(fused_exact_d(tab_c64, k, ev, pol_keep));
+}
+__device__ __noinline__ void fused_jacobi4(const double *Rw, double *vw, const bool active, const int j) { herm_eig4_coop(Rw, vw, active, j); }
+
+// One steering-table row against FZ_DG windows: scan_bin's hot path (music_kernels.cuh) with the rare exact evaluation
+// out of line.  Same arithmetic, same decisions: bit-identical results.
+__device__ __forceinline__ void drain_bin(const double (&ar)[4], const double (&ai)[4], const double na, const int k,
+                                          const uint32_t (&ev)[4], PeakState<4> &ps, const float *__restrict__ tab_c64,
+                                          const uint64_t pol_keep)
+{
+    constexpr int sig = 16 * 3 * 4;  // byte offset of the signal vector (largest eigenvalue)
+    double cr[4], ci[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double e0x;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(e0x) : "r"(ev[b] + sig));
+        cr[b] = e0x * ar[0];
+        ci[b] = e0x * ai[0];
+    }
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double2 e = lds_f64x2(ev[b] + sig + 16 * i);
+            cr[b] = fma(e.y, ai[i], cr[b]);
+            ci[b] = fma(-e.y, ar[i], ci[b]);
+            cr[b] = fma(e.x, ar[i], cr[b]);
+            ci[b] = fma(e.x, ai[i], ci[b]);
+        }
+    }
+    const int hg = __double2hiint(COMPLEMENT_GUARD * na);
+    unsigned cold = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double d = fma(-cr[b], cr[b], fma(-ci[b], ci[b], na));
+        const int hds = __double2hiint(d);
+        const unsigned hd = (unsigned)hds;
+        const bool guard = hds <= hg;
+        if ((hd - ps.hbm1[b]) <= 1u || guard) cold |= 1u << b;
+        if (hd < ps.hbm1[b] && !guard) { ps.bestd[b] = d; ps.bestk[b] = k; ps.hbm1[b] = max(hd, 1u) - 1u; }
+    }
+    if (cold) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (cold & (1u << b)) {
+                const double d = fused_exact_d(tab_c64, k, ev[b], pol_keep);
+                if (d < ps.bestd[b] && fused_recip_greater(d, ps.bestd[b])) {
+                    ps.bestd[b] = d;
+                    ps.bestk[b] = k;
+                    ps.hbm1[b] = max((unsigned)__double2hiint(d), 1u) - 1u;
+                }
+            }
+        }
+    }
 }
 
 // ---- shared-memory spin lock (one lane per warp contends) ----
@@ -241,10 +314,17 @@ __device__ __forceinline__ void fused_retire(unsigned char *smem, const unsigned
 }
 
 // Drain worker (a whole warp; see the file header): takes (group, bin chunk) units of an all-fp64 scan until every
-// window of this CTA has been handed out.  soa: the fp64 steering table of the unfused kernels ([tile][2M+1][TILE],
-// padding rows ||a||^2 = +inf).  Returns the number of units this warp processed.
-__device__ __noinline__ int fused_drain_worker(unsigned char *smem, const double *__restrict__ soa, const int K, const PeakOut out)
+// window of this CTA has been handed out.  The table is the complex64 one the block was given (32 bytes per bin; it is
+// also what the exact phase of the tensor-core passes reads, so it is L2-resident), widened here, ||a||^2 in the fma
+// order of the table preparation.  A group is FZ_DG windows (one table row serves four windows) - fewer only for the
+// CTA's very last windows; its FZ_NCH units interleave the table in steps of 32 bins (unit c: bins (i * FZ_NCH + c) * 32
+// + lane, i = 0, 1, ..), the next row is requested before the current one is evaluated.  Returns the number of units
+// this warp processed.
+template <bool TRACE>
+__device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float *__restrict__ tab_c64, const unsigned idle_ns, const int K,
+                                               const PeakOut out, long long *__restrict__ dbg_in, const long long t_start)
 {
+    long long *const dbg_cta = TRACE ? dbg_in : nullptr;
     FusedCtl *ctl = reinterpret_cast<FusedCtl *>(smem + FZ_OFF_CTL);
     DrainGroup *grp = reinterpret_cast<DrainGroup *>(smem + FZ_OFF_DGRP);
     double *resP = reinterpret_cast<double *>(smem + FZ_OFF_DRES);
@@ -252,12 +332,14 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const double
     const int *qwin = reinterpret_cast<const int *>(smem + FZ_OFF_WIN);
     const uint32_t Vq0 = smem_u32(smem + FZ_OFF_VQ);
     const int lane = threadIdx.x & 31;
-    const int CB = (K + FZ_NCH * 32 - 1) / (FZ_NCH * 32) * 32;  // bins per chunk
-    const int Kpad = (K + TILE - 1) / TILE * TILE;
     int units = 0;
+    long long ph[4] = {0, 0, 0, 0};  // trace: table sweep | merge + publish | whole unit | waiting for a unit
+    const uint64_t pol_keep = l2_policy_evict_last();
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // outputs are written in stream order (no-op once the previous grid is done)
     for (;;) {
         int slot = -1, chunk = 0, gc = 0;
         unsigned gs = 0;
+        const long long tw0 = dbg_cta ? clock64() : 0;
         if (lane == 0) {
             for (;;) {
                 bool all_done = false;
@@ -267,7 +349,10 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const double
                     slot = cur; chunk = (int)grp[cur].next_chunk++; gs = grp[cur].gs; gc = grp[cur].gc;
                 } else if (ctl->mma_off) {
                     const unsigned start = ctl->claim, avail = ctl->eig_done - start;
-                    if (avail > 0) {
+                    // every window of this CTA has its eigenvectors: what is left may go out as a partial group
+                    const bool last = ctl->cov_finished == (unsigned)FZ_COV_WARPS &&
+                                      ctl->eig_done == *reinterpret_cast<volatile unsigned *>(&ctl->cov_seq);
+                    if (avail >= (unsigned)FZ_DG || (avail > 0 && last)) {
                         int f = -1;
                         for (int i = 0; i < FZ_NGS; ++i)
                             if (!grp[i].busy) { f = i; break; }
@@ -277,81 +362,118 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const double
                             ctl->claim = start + gc;
                             ctl->dg_open = f;
                             ctl->drained_windows += gc;
+                            ctl->drain_groups += 1;
                             slot = f; chunk = 0; gs = start;
                         }
-                    } else {
-                        all_done = ctl->cov_finished == (unsigned)FZ_COV_WARPS &&
-                                   ctl->eig_done == *reinterpret_cast<volatile unsigned *>(&ctl->cov_seq);
+                    } else if (avail == 0) {
+                        all_done = last;
                     }
                 }
                 fz_unlock(ctl);
                 if (slot >= 0) break;
                 if (all_done) { slot = -2; break; }
-                __nanosleep(100);
+                __nanosleep(idle_ns);
             }
         }
         slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot < 0) return units;
+        if (dbg_cta && lane == 0) ph[3] += clock64() - tw0;
+        if (slot < 0) {
+            if (dbg_cta && lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 22), (unsigned long long)ph[2]);
+                atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 25), (unsigned long long)ph[0]);
+                atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 26), (unsigned long long)ph[1]);
+                atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 28), (unsigned long long)ph[3]);
+                atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 29), (unsigned long long)units);
+            }
+            return units;
+        }
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         gc = __shfl_sync(0xffffffffu, gc, 0);
         gs = __shfl_sync(0xffffffffu, gs, 0);
         ++units;
+        const long long tu0 = dbg_cta ? clock64() : 0;
         uint32_t ev[FZ_DG];
 #pragma unroll
         for (int b = 0; b < FZ_DG; ++b) ev[b] = Vq0 + 256u * ((gs + (unsigned)min(b, gc - 1)) % FZ_Q);
         PeakState<FZ_DG> ps;
         ps.reset();
-        const int k1 = min((chunk + 1) * CB, Kpad);
-        for (int k = chunk * CB + lane; k < k1; k += 32) {
-            const double *tb = soa + (size_t)(k / TILE) * 9 * TILE + (k % TILE);
-            double ar[4], ai[4];
+        double ar[4], ai[4], na = 0.0, nr[4], ni[4], nna = 0.0;
+        auto load_row = [&](const int k, double (&r)[4], double (&im)[4], double &n) {  // k < K
+            const float4 *row = reinterpret_cast<const float4 *>(tab_c64 + (size_t)k * 8);
+            const float4 x0 = ldg_f32x4_hint(row, pol_keep), x1 = ldg_f32x4_hint(row + 1, pol_keep);
+            r[0] = x0.x; im[0] = x0.y; r[1] = x0.z; im[1] = x0.w;
+            r[2] = x1.x; im[2] = x1.y; r[3] = x1.z; im[3] = x1.w;
+            double a = 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                ar[i] = __ldg(tb + (size_t)(2 * i) * TILE);
-                ai[i] = __ldg(tb + (size_t)(2 * i + 1) * TILE);
-            }
-            const double na = __ldg(tb + (size_t)8 * TILE);
-            scan_bin<4, FZ_DG>(ar, ai, na, k, ev, ps);
+            for (int i = 0; i < 4; ++i) a = fma(r[i], r[i], fma(im[i], im[i], a));
+            n = a;
+        };
+        int k = chunk * 32 + lane;
+        if (k < K) load_row(k, ar, ai, na);
+#pragma unroll 1
+        while (k < K) {
+            const int kn = k + FZ_NCH * 32;
+            if (kn < K) load_row(kn, nr, ni, nna);
+            drain_bin(ar, ai, na, k, ev, ps, tab_c64, pol_keep);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ar[i] = nr[i]; ai[i] = ni[i]; }
+            na = nna;
+            k = kn;
         }
-        // per-window merge over the lanes, order (P desc, bin asc)
+        __syncwarp();
+        long long tp2 = 0;
+        if (dbg_cta) { asm volatile("" ::"d"(ps.bestd[0]), "d"(ps.bestd[3]), "r"(ps.bestk[1]) : "memory"); tp2 = clock64(); }
+        // per-window merge over the lanes, order (P desc, bin asc); a lane without a bin holds d = +inf -> P = 0, bin -1.
+        // Three warp reductions per window (redux.sync) instead of a 5-round shuffle butterfly: non-negative doubles
+        // order like their bit patterns, so max(high word), then max(low word) among the lanes that hold it, then
+        // min(bin) among the lanes that hold both.
+        double P[FZ_DG];
+        int kk[FZ_DG];
 #pragma unroll
         for (int b = 0; b < FZ_DG; ++b) {
-            int kk = ps.bestk[b];
-            double P = kk >= 0 ? 1.0 / ps.bestd[b] : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double Po = __shfl_xor_sync(0xffffffffu, P, o);
-                const int ko = __shfl_xor_sync(0xffffffffu, kk, o);
-                if (peak_better(Po, ko, P, kk)) { P = Po; kk = ko; }
-            }
-            if (lane == 0) {
-                resP[(slot * FZ_NCH + chunk) * FZ_DG + b] = P;
-                resk[(slot * FZ_NCH + chunk) * FZ_DG + b] = kk;
-            }
+            const double Pl = fused_recip(ps.bestd[b]);
+            const unsigned hi = (unsigned)__double2hiint(Pl), lo = (unsigned)__double2loint(Pl);
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+            const unsigned mk = __reduce_min_sync(0xffffffffu, (hi == mh && lo == ml && ps.bestk[b] >= 0) ? (unsigned)ps.bestk[b] : 0x7fffffffu);
+            P[b] = __hiloint2double((int)mh, (int)ml);
+            kk[b] = mk == 0x7fffffffu ? -1 : (int)mk;
         }
         int last = 0;
         if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < FZ_DG; ++b) {
+                resP[(slot * FZ_NCH + chunk) * FZ_DG + b] = P[b];
+                resk[(slot * FZ_NCH + chunk) * FZ_DG + b] = kk[b];
+            }
             __threadfence_block();
             last = atomicAdd(&grp[slot].done, 1u) == (unsigned)FZ_NCH - 1 ? 1 : 0;
             __threadfence_block();
+            if (dbg_cta) {  // phases of this unit, accumulated in registers and written once when the worker returns
+                const long long tp4 = clock64();
+                ph[0] += tp2 - tu0; ph[1] += tp4 - tp2; ph[2] += tp4 - tu0;
+            }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
-            // this warp finished the group's last unit: merge the chunks in ascending order (lane b <-> window b)
+            // this warp finished the group's last unit: merge the chunks (lane b <-> window b; any order gives the same
+            // result, (P desc, bin asc) is a total order)
             if (lane < gc) {
-                double P = resP[(slot * FZ_NCH) * FZ_DG + lane];
-                int kk = resk[(slot * FZ_NCH) * FZ_DG + lane];
+                double Pm = resP[(slot * FZ_NCH) * FZ_DG + lane];
+                int km = resk[(slot * FZ_NCH) * FZ_DG + lane];
+#pragma unroll 1
                 for (int c = 1; c < FZ_NCH; ++c) {
                     const double Pc = resP[(slot * FZ_NCH + c) * FZ_DG + lane];
                     const int kc = resk[(slot * FZ_NCH + c) * FZ_DG + lane];
-                    if (peak_better(Pc, kc, P, kk)) { P = Pc; kk = kc; }
+                    if (peak_better(Pc, kc, Pm, km)) { Pm = Pc; km = kc; }
                 }
-                fused_write_peak(out, (size_t)qwin[(gs + lane) % FZ_Q], kk, P, K);
+                fused_write_peak(out, (size_t)qwin[(gs + lane) % FZ_Q], km, Pm, K);
             }
             __syncwarp();
             if (lane == 0) {
                 fused_retire(smem, gs, (unsigned)gc);
                 grp[slot].busy = 0;  // (results were read above; a new group may reuse the slot)
+                if (dbg_cta) dbg_cta[23] = clock64() - t_start;  // (the last group to finish writes last)
             }
             __syncwarp();
         }
@@ -362,18 +484,23 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const double
 // [first_snapshot + w * hop, ... + N) of each stream - by four 1 KiB bulk copies per stage instead of one 4 KiB copy;
 // the stage then holds [antenna][128 snapshots] and a lane gathers its snapshot with four LDS.64.  Requires 16-byte
 // aligned streams and even first_snapshot, hop and N (bulk copies move multiples of 16 bytes).
-template <bool PLANAR>
+// TRACE = true: the instantiation tools/fused_trace.py runs (MUSIC_B200_TRACE=1): per-CTA clock64 trace in dbg_in.
+template <bool PLANAR, bool TRACE>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigned long long first_snapshot, unsigned hop,
                     const unsigned char *__restrict__ tbl /* fused_table_bytes(K) */,
                     const float *__restrict__ tab_c64 /* [K][4] complex64 */, const float *__restrict__ na_max_p, int W, int N,
                     int K, PeakOut out, unsigned *__restrict__ work_ctr /* [0]: window tickets, [1]: finished CTAs; both zero between launches */,
-                    long long *__restrict__ dbg /* optional [grid][16] clock64 trace, may be null */,
-                    const int eig_mode /* 0: principal eigenvector by squaring (Jacobi fallback), 1: Jacobi with four lanes per window, 2: Jacobi with one lane per window */,
-                    const double *__restrict__ soa /* fp64 steering table of the unfused kernels (drain workers) */,
+                    long long *__restrict__ dbg_in /* TRACE: [grid][FZ_TRACE] clock64 trace */,
+                    const int eig_mode /* 0: principal eigenvector by squaring (Jacobi fallback), otherwise: Jacobi, four lanes per window */,
                     const GatherFlags gather_flags /* epoch flags of the fused bins all-gather (out.npeer > 0) */,
-                    const int mma_fin_max /* tensor-core passes start only while at most this many covariance warps are done; < 0: never */)
+                    const int mma_fin_max /* tensor-core passes start only while at most this many covariance warps are done; < 0: never */,
+                    const unsigned idle_ns /* sleep of a drain worker that found no unit */)
 {
+    long long *const dbg = TRACE ? dbg_in : nullptr;
+    // programmatic dependent launch: the next launch on this stream may take the SMs this grid leaves (it needs a whole
+    // SM per CTA, so it cannot disturb a running one); see griddepcontrol.wait below for the other half
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long t_start = clock64();
     unsigned long long g_start = 0;
     if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
@@ -391,9 +518,10 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
     }
     if (threadIdx.x < FZ_NGS * 8) reinterpret_cast<unsigned *>(fz_smem + FZ_OFF_DGRP)[threadIdx.x] = 0u;
     if (threadIdx.x == 0) {
+        if (dbg) { dbg[blockIdx.x * FZ_TRACE + 22] = 0; for (int i = 24; i < 30; ++i) dbg[blockIdx.x * FZ_TRACE + i] = 0; }  // (accumulated by the drain workers)
         ctl->cov_seq = 0; ctl->lock = 0; ctl->eig_done = 0; ctl->scan_done = 0; ctl->cov_finished = 0;
         ctl->batch_start = 0; ctl->batch_cnt = 0; ctl->claim = 0; ctl->tout = 0; ctl->mma_off = mma_fin_max < 0 ? 1u : 0u;
-        ctl->dg_open = -1; ctl->drained_windows = 0;
+        ctl->dg_open = -1; ctl->drained_windows = 0; ctl->drain_groups = 0;
         const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR);
         for (int s = 0; s < FZ_TS; ++s) {
             mbar_init(tb0 + 8 * s, FZ_SCAN_THREADS);            // tfull: one cp.async-completion arrival per scan thread
@@ -426,6 +554,10 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
         __syncwarp();
         // producer state (lane 0): next chunk to request = chunk iq of window iw (-1: stream exhausted)
         int iq = 0, iw = -1, islot = 0, wr = 0;
+        // the stream is read once: evict_first, so that it does not push the steering tables out of L2 (overlapping
+        // planar windows, hop < N, are re-read from L2 by the next windows and keep the default policy)
+        const bool stream_once = !PLANAR || hop >= (unsigned)N;
+        const uint64_t pol_stream = l2_policy_evict_first();
         auto claim = [&]() {
             const unsigned tkt = atomicAdd(ctr, 1u);
             iw = tkt < (unsigned)W ? (int)tkt : -1;
@@ -441,10 +573,12 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             if (PLANAR) {
                 const unsigned long long s0 = first_snapshot + (unsigned long long)iw * hop + (unsigned long long)iq * (COV_CHUNK / 32);
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    bulk_g2s(ring0 + islot * COV_CHUNK + r * (COV_CHUNK / 4), S.p[r] + s0, bytes / 4, bar0 + 8 * islot);
+                for (int r = 0; r < 4; ++r) {
+                    if (stream_once) bulk_g2s_hint(ring0 + islot * COV_CHUNK + r * (COV_CHUNK / 4), S.p[r] + s0, bytes / 4, bar0 + 8 * islot, pol_stream);
+                    else bulk_g2s(ring0 + islot * COV_CHUNK + r * (COV_CHUNK / 4), S.p[r] + s0, bytes / 4, bar0 + 8 * islot);
+                }
             } else {
-                bulk_g2s(ring0 + islot * COV_CHUNK, src0 + (size_t)iw * win_bytes + off, bytes, bar0 + 8 * islot);
+                bulk_g2s_hint(ring0 + islot * COV_CHUNK, src0 + (size_t)iw * win_bytes + off, bytes, bar0 + 8 * islot, pol_stream);
             }
             if (++islot == FZ_STAGES) islot = 0;
             if (++iq == cpw) { iq = 0; claim(); }
@@ -531,7 +665,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             if (dbg && fin == 0) dbg[blockIdx.x * FZ_TRACE + 1] = clock64() - t_start;                           // first one
         }
         __syncwarp();
-        fused_drain_worker(fz_smem, soa, K, out);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0, eig_jacobi = 0;
@@ -548,9 +682,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             }
             __threadfence_block();
             const long long t0 = clock64();
-            unsigned cnt;
-            if (eig_mode <= 1) {
-                cnt = min(avail, 8u);
+            const unsigned cnt = min(avail, 8u);
+            {
                 const unsigned grp = (unsigned)lane >> 2;
                 const unsigned slot = (done + min(grp, cnt - 1)) % FZ_Q;
                 bool jac = grp < cnt;  // windows the Jacobi solver must take
@@ -559,14 +692,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     jac = jac && !solved;
                 }
                 if (__any_sync(0xffffffffu, jac)) {
-                    herm_eig4_coop(Rq + (size_t)slot * 32, Vq + (size_t)slot * 32, jac, lane & 3);
+                    fused_jacobi4(Rq + (size_t)slot * 32, Vq + (size_t)slot * 32, jac, lane & 3);
                     ++eig_jacobi;
-                }
-            } else {
-                cnt = min(avail, 8u);
-                if ((unsigned)lane < cnt) {
-                    const unsigned slot = (done + lane) % FZ_Q;
-                    herm_eig_body<4, true>(Rq + (size_t)slot * 32, nullptr, Vq + (size_t)slot * 32, 4);
                 }
             }
             __syncwarp();
@@ -582,7 +709,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 10] = eig_rounds;
             dbg[blockIdx.x * FZ_TRACE + 19] = eig_jacobi;
         }
-        fused_drain_worker(fz_smem, soa, K, out);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else {
         // ================= scan warps =================
         const int st = threadIdx.x - 32 * (FZ_COV_WARPS + 1);  // 0..223
@@ -597,9 +724,14 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
         const int ntile_full = fused_tiles(K);
         const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR), tbuf0 = smem_u32(fz_smem + FZ_OFF_TBL);
         const float na_max = __ldg(na_max_p);
+        const uint64_t pol_keep = l2_policy_evict_last();
         unsigned T = 0;  // table tiles consumed so far (identical in every scan thread)
         long long scan_busy = 0, scan_passes = 0, scan_exact = 0, scan_fallbacks = 0, scan_ncand = 0;
         long long tr_issue = 0, tr_full = 0, tr_comp = 0;
+        // Output writes must land after those of the previous launch on the stream (which may still be draining on other
+        // SMs under programmatic dependent launch): the writers wait for it here - the covariance warps do not, the
+        // 64-slot queue absorbs the few microseconds this can take.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 
         for (;;) {
             if (st == 0) {
@@ -654,8 +786,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                 bh0[gi] = to_tf32(v0); bl0[gi] = to_tf32(v0 - __uint_as_float(bh0[gi]));
                 bh1[gi] = to_tf32(v1); bl1[gi] = to_tf32(v1 - __uint_as_float(bh1[gi]));
             }
-            // One sweep over the table through the FZ_TS-deep ring; f(gi, row, d~, ||a||^2) for this thread's two rows
-            // (g, g + 8) of every MMA tile it owns and both column groups (its windows are 4*gi + t).
+            // The table streams through the FZ_TS-deep ring; every thread handles two rows (g, g + 8) of every MMA tile its
+            // warp owns and both column groups (its windows are 4*gi + t).
             // T counts tiles since kernel start: slot = T % FZ_TS, tfull parity = (T / FZ_TS) & 1; a tile is
             // released by one arrival per scan warp on tempty.
             // Table tiles arrive by cp.async (LDGSTS, 16 B per request through the LSU): the SM's TMA queue is FIFO
@@ -672,12 +804,24 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                 for (int c = 0; c < FZ_CPT; ++c) {
                     const int chunk = st + c * FZ_SCAN_THREADS;  // 16-byte chunk of the tile
                     if (chunk < FZ_TILE_BYTES / 16)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * chunk), "l"(src + 16 * chunk) : "memory");
+                        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + 16 * chunk), "l"(src + 16 * chunk), "l"(pol_keep) : "memory");
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tb0 + 8 * sa) : "memory");
             };
-            auto sweep = [&](const int tile0, const int ntile, const int rstride, auto &&f) {
+            // ---- the two sweeps of a pass share ONE loop body (instruction footprint, see the file header) ----
+            //   phase 0 (the decimated tiles only): an upper bound U >= min_k d_k per window, U = min over the subsample
+            //           of d~ + B||a||^2 (any bin's upper bound bounds the minimum from above);
+            //   phase 1 (the whole table): the candidates, lower bound d~ - B||a||^2 <= U (1 + 2^-10); the relative slack
+            //           makes every rejected bin's exact d larger than the best one's by > 2^-11 relative, so its
+            //           reciprocal is strictly smaller (no tie can be lost to the rounding of 1/d).  Columns that
+            //           duplicate a window (beyond cnt) do not report.
+            const float INF = __int_as_float(0x7f800000);
+            float umin[2] = {INF, INF}, thr[2] = {-INF, -INF};
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+                const int tile0 = phase ? FZ_NDEC : 0, ntile = phase ? ntile_full : FZ_NDEC;
                 for (int a = 0; a < D && a < ntile; ++a) issue_tile(tile0 + a, T + a);
+#pragma unroll 1
                 for (int it = 0; it < ntile; ++it, ++T) {
                     const int slot = (int)(T % FZ_TS);
                     const long long tk0 = dbg ? clock64() : 0;
@@ -686,7 +830,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     while (!mbar_try_wait(tb0 + 8 * slot, (uint32_t)((T / FZ_TS) & 1))) {}
                     const long long tk2 = dbg ? clock64() : 0;
                     const uint32_t tile = tbuf0 + slot * FZ_TILE_BYTES;
-                    // both MMA tiles of this warp: loads and the truncating tf32 split (ALU pipe) first
+                    // all MMA tiles of this warp: loads and the truncating tf32 split (ALU pipe) first
                     uint32_t ah[FZ_MPW][4], al[FZ_MPW][4];
                     float na0[FZ_MPW], na1[FZ_MPW];
 #pragma unroll
@@ -704,8 +848,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tb0 + 8 * (FZ_TS + slot)) : "memory");
-                    // 12 MMAs = 3 (a_lo e_hi, a_hi e_lo, a_hi e_hi; small terms first) for each of the 4 (tile, column
-                    // group) accumulators, issued round-robin so that dependent MMAs are 4 instructions (~32
+                    // 3 MMAs (a_lo e_hi, a_hi e_lo, a_hi e_hi; small terms first) for each of the 2 FZ_MPW (tile, column
+                    // group) accumulators, issued round-robin so that dependent MMAs are 8 instructions (~64
                     // cycles at one HMMA.1688 per 8 cycles) apart - more than the ~20-cycle MMA latency.
                     float c[FZ_MPW][2][4];
 #pragma unroll
@@ -729,54 +873,57 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                             asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                 : "+f"(c[m][gi][0]), "+f"(c[m][gi][1]), "+f"(c[m][gi][2]), "+f"(c[m][gi][3])
                                 : "r"(ah[m][0]), "r"(ah[m][1]), "r"(ah[m][2]), "r"(ah[m][3]), "r"(bh0[gi]), "r"(bh1[gi]));
+                    // (c0, c1) = (Re, Im) of e^H a for row g, window 4*gi + t; (c2, c3) the same for row g + 8
+                    if (phase == 0) {
 #pragma unroll
-                    for (int m = 0; m < FZ_MPW; ++m) {
-                        const int row = (it * FZ_BINS + (m * FZ_SCAN_WARPS + swarp) * 16 + g) * rstride;
+                        for (int m = 0; m < FZ_MPW; ++m)
 #pragma unroll
-                        for (int gi = 0; gi < 2; ++gi) {
-                            // (c0, c1) = (Re, Im) of e^H a for row g, window 4*gi + t; (c2, c3) the same for row g + 8
-                            f(gi, row, na0[m] - fmaf(c[m][gi][0], c[m][gi][0], c[m][gi][1] * c[m][gi][1]), na0[m]);
-                            f(gi, row + 8 * rstride, na1[m] - fmaf(c[m][gi][2], c[m][gi][2], c[m][gi][3] * c[m][gi][3]), na1[m]);
+                            for (int gi = 0; gi < 2; ++gi) {
+                                const float d0 = na0[m] - fmaf(c[m][gi][0], c[m][gi][0], c[m][gi][1] * c[m][gi][1]);
+                                const float d1 = na1[m] - fmaf(c[m][gi][2], c[m][gi][2], c[m][gi][3] * c[m][gi][3]);
+                                umin[gi] = fminf(umin[gi], fminf(fmaf(FZ_B, na0[m], d0), fmaf(FZ_B, na1[m], d1)));
+                            }
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < FZ_MPW; ++m) {
+                            const int row = it * FZ_BINS + (m * FZ_SCAN_WARPS + swarp) * 16 + g;
+#pragma unroll
+                            for (int gi = 0; gi < 2; ++gi) {
+                                const float d0 = na0[m] - fmaf(c[m][gi][0], c[m][gi][0], c[m][gi][1] * c[m][gi][1]);
+                                const float d1 = na1[m] - fmaf(c[m][gi][2], c[m][gi][2], c[m][gi][3] * c[m][gi][3]);
+                                if (fmaf(-FZ_B, na0[m], d0) <= thr[gi]) {
+                                    const int sc = atomicAdd(&cand_cnt[4 * gi + t], 1);
+                                    if (sc < FZ_CMAX) cand_bin[(4 * gi + t) * FZ_CMAX + sc] = row;
+                                }
+                                if (fmaf(-FZ_B, na1[m], d1) <= thr[gi]) {
+                                    const int sc = atomicAdd(&cand_cnt[4 * gi + t], 1);
+                                    if (sc < FZ_CMAX) cand_bin[(4 * gi + t) * FZ_CMAX + sc] = row + 8;
+                                }
+                            }
                         }
                     }
                     if (dbg) { const long long tk3 = clock64(); tr_issue += tk1 - tk0; tr_full += tk2 - tk1; tr_comp += tk3 - tk2; }
                 }
-            };
-
-            // ---- sweep 1 (the decimated tile only): an upper bound U >= min_k d_k per window, U = min over the
-            // subsample of d~ + B||a||^2 (any bin's upper bound bounds the minimum from above) ----
-            const float INF = __int_as_float(0x7f800000);
-            float umin[2] = {INF, INF};
-            sweep(0, FZ_NDEC, fused_stride(K), [&](const int gi, const int, const float d, const float na) { umin[gi] = fminf(umin[gi], fmaf(FZ_B, na, d)); });
+                if (phase == 0) {
 #pragma unroll
-            for (int gi = 0; gi < 2; ++gi) {
-                float u = umin[gi];
-                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 4));
-                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 8));
-                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 16));
-                if (lane < 4) redmin[swarp * FZ_WPT + 4 * gi + lane] = u;
-            }
-            bar_sync_scan();
-            // candidates: lower bound d~ - B||a||^2 <= U (1 + 2^-10); the relative slack makes every rejected bin's
-            // exact d larger than the best one's by > 2^-11 relative, so its reciprocal is strictly smaller (no tie
-            // can be lost to the rounding of 1/d).  Columns that duplicate a window (beyond cnt) do not report.
-            float thr[2];
+                    for (int gi = 0; gi < 2; ++gi) {
+                        float u = umin[gi];
+                        u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 4));
+                        u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 8));
+                        u = fminf(u, __shfl_xor_sync(0xffffffffu, u, 16));
+                        if (lane < 4) redmin[swarp * FZ_WPT + 4 * gi + lane] = u;
+                    }
+                    bar_sync_scan();
 #pragma unroll
-            for (int gi = 0; gi < 2; ++gi) {
-                const int w = 4 * gi + t;
-                float u = redmin[w];
+                    for (int gi = 0; gi < 2; ++gi) {
+                        const int w = 4 * gi + t;
+                        float u = redmin[w];
 #pragma unroll
-                for (int q = 1; q < FZ_SCAN_WARPS; ++q) u = fminf(u, redmin[q * FZ_WPT + w]);
-                thr[gi] = (unsigned)w < cnt ? fmaf(fabsf(u), 0.0009765625f, u) : -INF;
-            }
-
-            // ---- sweep 2 (the whole table): collect the candidates ----
-            sweep(FZ_NDEC, ntile_full, 1, [&](const int gi, const int row, const float d, const float na) {
-                if (fmaf(-FZ_B, na, d) <= thr[gi]) {
-                    const int s = atomicAdd(&cand_cnt[4 * gi + t], 1);
-                    if (s < FZ_CMAX) cand_bin[(4 * gi + t) * FZ_CMAX + s] = row;
+                        for (int q = 1; q < FZ_SCAN_WARPS; ++q) u = fminf(u, redmin[q * FZ_WPT + w]);
+                        thr[gi] = (unsigned)w < cnt ? fmaf(fabsf(u), 0.0009765625f, u) : -INF;
+                    }
                 }
-            });
+            }
             bar_sync_scan();
 
             // ---- exact fp64 evaluation: the candidates of all windows flattened over the scan threads ----
@@ -808,7 +955,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
 #pragma unroll
                     for (int q = 1; q < FZ_WPT; ++q) w += (i >= pre[q]) ? 1 : 0;
                     const int k = cand_bin[w * FZ_CMAX + (i - pre[w])];
-                    const double P = fused_exact_P(tab_c64, k, Vq0 + 256 * ((start + w) % FZ_Q));
+                    const double P = fused_exact_P(tab_c64, k, Vq0 + 256 * ((start + w) % FZ_Q), pol_keep);
                     if (P > 0.0) {  // NaN and non-positive strengths are never inserted (reference :132)
                         myP[r] = P; myk[r] = k; myw[r] = w;
                         atomicMax(&bestP[w], (unsigned long long)__double_as_longlong(P));
@@ -842,7 +989,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                 double P = 0.0;
                 int kk = -1;
                 for (int k = st; k < K; k += FZ_SCAN_THREADS) {
-                    const double p = fused_exact_P(tab_c64, k, ev);
+                    const double p = fused_exact_P(tab_c64, k, ev, pol_keep);
                     if (p > P) { P = p; kk = k; }  // k ascending per thread: strict '>' keeps the lower bin
                 }
 #pragma unroll
@@ -890,7 +1037,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 3] = (long long)(g_end - g_start);   // ns, this CTA's lifetime (overwrites covariance warp 3's slot)
             dbg[blockIdx.x * FZ_TRACE + 2] = (long long)g_start;             // ns, absolute start (overwrites covariance warp 2's slot)
         }
-        fused_drain_worker(fz_smem, soa, K, out);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     }
     // The last CTA to finish re-arms the ticket counter for the next launch (launches of one handle are
     // serialised by the host, and by now every covariance warp has drawn a ticket >= W).
@@ -898,6 +1045,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
     if (threadIdx.x == 0) {
         if (dbg) {
             dbg[blockIdx.x * FZ_TRACE + 17] = ctl->drained_windows;
+            dbg[blockIdx.x * FZ_TRACE + 20] = ctl->drain_groups;
             dbg[blockIdx.x * FZ_TRACE + 18] = clock64() - t_start;  // every window of this CTA is finished
         }
         if (out.npeer > 0) __threadfence_system(); else __threadfence();
@@ -910,7 +1058,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             if (out.npeer > 0 && gather_flags.epoch) {
                 __threadfence_system();
                 for (int p = 0; p < out.npeer; ++p)
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(gather_flags.peer[p] + out.rank), "r"(gather_flags.epoch) : "memory");
+                    asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(gather_flags.peer[p] + out.rank), "r"(gather_flags.epoch) : "memory");  // (max: launches may retire out of order)
             }
         }
     }

@@ -218,12 +218,13 @@ music8_fused_kernel(const __grid_constant__ CUtensorMap tm, const double *__rest
         wring[wr & 7] = iw;
         ++wr;
     };
+    const uint64_t pol_stream = l2_policy_evict_first();
     auto issue = [&]() {  // the slot is free: the only consumer is this warp, in program order
         const int slot = (int)(issued % F8_SG);
         mbar_expect_tx(full0 + 8 * slot, F8_STAGE);
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                     ::"r"(ring0 + slot * F8_STAGE), "l"(tm_addr), "r"(0), "r"(iq * (F8_STAGE / 128)), "r"(iw), "r"(full0 + 8 * slot)
-                     : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                     ::"r"(ring0 + slot * F8_STAGE), "l"(tm_addr), "r"(0), "r"(iq * (F8_STAGE / 128)), "r"(iw), "r"(full0 + 8 * slot), "l"(pol_stream)
+                     : "memory");  // evict_first: the stream is read once and must not push the steering table out of L2
         ++issued;
         if (++iq == cpw) { iq = 0; claim(); }
     };

@@ -368,7 +368,9 @@ def test_fused_m8_kernel_matches_unfused_path_and_oracle(monkeypatch, base, over
         assert got[4] == 1 + 2 and ref[4] > got[4]  # table preparation + ONE launch per call
         assert got[3][0] + got[3][1] == 2 * nw
         if nw == W:
-            assert 2 * 4 <= got[3][1] <= 2 * 12  # the degenerate windows (and few others) took the Jacobi fallback
+            # the all-zero window must take the Jacobi fallback (no trace to scale by); noise-only windows may converge
+            # by squaring (an eigenvalue ratio of 1.02 becomes 1.02^4096 after 12 squarings) or fall back
+            assert 2 * 1 <= got[3][1] <= 2 * 12
         assert np.array_equal(got[2], ref[2]) and np.array_equal(got[0], ref[0])
         assert helpers.rel_err(got[1], ref[1]) <= 1e-9
         jac = run(True, "jacobi", nw)
