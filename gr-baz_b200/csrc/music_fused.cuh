@@ -273,16 +273,26 @@ __device__ __forceinline__ void drain_bin(const double (&ar)[4], const double (&
     }
 }
 
-// ---- shared-memory spin lock (one lane per warp contends) ----
-__device__ __forceinline__ void fz_lock(FusedCtl *ctl)
+// ---- shared-memory spin lock ----
+// WARP-UNIFORM CONTROL FLOW.  Every wait in this kernel is a loop that ALL lanes of the warp run, with lane 0 doing the
+// atomic / the polling read and the outcome broadcast by __shfl_sync.  The first version let lane 0 spin alone inside
+// `if (lane == 0) { for (;;) { lock ... __nanosleep } }`: after such a block the warp stayed split (lane 0 | lanes 1-31,
+// measured with __activemask() in the TRACE build: every drain unit ran twice, every warp collective took its
+// divergent slow path - 26 k cycles for a 60-shuffle merge).
+__device__ __forceinline__ void fz_lock(FusedCtl *ctl, const int lane)  // all lanes call; lane 0 holds the lock afterwards
 {
-    while (atomicCAS(&ctl->lock, 0u, 1u) != 0u) {}
+    for (;;) {
+        unsigned got = 0u;
+        if (lane == 0) got = atomicCAS(&ctl->lock, 0u, 1u) == 0u ? 1u : 0u;
+        if (__shfl_sync(0xffffffffu, got, 0)) break;
+    }
     __threadfence_block();
 }
-__device__ __forceinline__ void fz_unlock(FusedCtl *ctl)
+__device__ __forceinline__ void fz_unlock(FusedCtl *ctl, const int lane)  // all lanes call
 {
     __threadfence_block();
-    atomicExch(&ctl->lock, 0u);
+    if (lane == 0) atomicExch(&ctl->lock, 0u);
+    __syncwarp();
 }
 
 // peak of one window -> the block's outputs (reference :134, :153-154; (0, 0) initial pair :95)
@@ -299,18 +309,20 @@ __device__ __forceinline__ void fused_write_peak(const PeakOut &out, const size_
 }
 
 // windows [start, start + cnt) are finished: mark their queue slots and advance scan_done over every finished slot
-// (tensor-core passes and drain groups complete out of order).  One thread.
-__device__ __forceinline__ void fused_retire(unsigned char *smem, const unsigned start, const unsigned cnt)
+// (tensor-core passes and drain groups complete out of order).  All lanes of one warp call.
+__device__ __forceinline__ void fused_retire(unsigned char *smem, const unsigned start, const unsigned cnt, const int lane)
 {
     FusedCtl *ctl = reinterpret_cast<FusedCtl *>(smem + FZ_OFF_CTL);
     volatile unsigned *qdone = reinterpret_cast<volatile unsigned *>(smem + FZ_OFF_QDONE);
     __threadfence_block();
-    fz_lock(ctl);
-    for (unsigned w = 0; w < cnt; ++w) qdone[(start + w) % FZ_Q] = 1u;
-    unsigned sd = ctl->scan_done;
-    while (sd != ctl->claim && qdone[sd % FZ_Q]) { qdone[sd % FZ_Q] = 0u; ++sd; }
-    ctl->scan_done = sd;
-    fz_unlock(ctl);
+    fz_lock(ctl, lane);
+    if (lane == 0) {
+        for (unsigned w = 0; w < cnt; ++w) qdone[(start + w) % FZ_Q] = 1u;
+        unsigned sd = ctl->scan_done;
+        while (sd != ctl->claim && qdone[sd % FZ_Q]) { qdone[sd % FZ_Q] = 0u; ++sd; }
+        ctl->scan_done = sd;
+    }
+    fz_unlock(ctl, lane);
 }
 
 // Drain worker (a whole warp; see the file header): takes (group, bin chunk) units of an all-fp64 scan until every
@@ -334,16 +346,17 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
     const int lane = threadIdx.x & 31;
     int units = 0;
     long long ph[4] = {0, 0, 0, 0};  // trace: table sweep | merge + publish | whole unit | waiting for a unit
+    int ndiv0 = 0, ndiv1 = 0;
     const uint64_t pol_keep = l2_policy_evict_last();
     asm volatile("griddepcontrol.wait;" ::: "memory");  // outputs are written in stream order (no-op once the previous grid is done)
     for (;;) {
         int slot = -1, chunk = 0, gc = 0;
         unsigned gs = 0;
         const long long tw0 = dbg_cta ? clock64() : 0;
-        if (lane == 0) {
-            for (;;) {
-                bool all_done = false;
-                fz_lock(ctl);
+        for (;;) {  // (all lanes loop; lane 0 decides inside the lock, the outcome is broadcast)
+            int all_done = 0;
+            fz_lock(ctl, lane);
+            if (lane == 0) {
                 const int cur = ctl->dg_open;
                 if (cur >= 0 && grp[cur].next_chunk < (unsigned)FZ_NCH) {
                     slot = cur; chunk = (int)grp[cur].next_chunk++; gs = grp[cur].gs; gc = grp[cur].gc;
@@ -366,16 +379,17 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
                             slot = f; chunk = 0; gs = start;
                         }
                     } else if (avail == 0) {
-                        all_done = last;
+                        all_done = last ? 1 : 0;
                     }
                 }
-                fz_unlock(ctl);
-                if (slot >= 0) break;
-                if (all_done) { slot = -2; break; }
-                __nanosleep(idle_ns);
             }
+            fz_unlock(ctl, lane);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            all_done = __shfl_sync(0xffffffffu, all_done, 0);
+            if (slot >= 0) break;
+            if (all_done) { slot = -2; break; }
+            __nanosleep(idle_ns);
         }
-        slot = __shfl_sync(0xffffffffu, slot, 0);
         if (dbg_cta && lane == 0) ph[3] += clock64() - tw0;
         if (slot < 0) {
             if (dbg_cta && lane == 0) {
@@ -384,6 +398,8 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
                 atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 26), (unsigned long long)ph[1]);
                 atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 28), (unsigned long long)ph[3]);
                 atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 29), (unsigned long long)units);
+                atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 24), (unsigned long long)ndiv0);
+                atomicAdd(reinterpret_cast<unsigned long long *>(dbg_cta + 27), (unsigned long long)ndiv1);
             }
             return units;
         }
@@ -409,6 +425,7 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
             n = a;
         };
         int k = chunk * 32 + lane;
+        if (TRACE && dbg_cta && __activemask() != 0xffffffffu) ++ndiv0;  // (trace: is the warp converged at the sweep?)
         if (k < K) load_row(k, ar, ai, na);
 #pragma unroll 1
         while (k < K) {
@@ -421,6 +438,7 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
             k = kn;
         }
         __syncwarp();
+        if (TRACE && dbg_cta && __activemask() != 0xffffffffu) ++ndiv1;  // (... and at the merge?)
         long long tp2 = 0;
         if (dbg_cta) { asm volatile("" ::"d"(ps.bestd[0]), "d"(ps.bestd[3]), "r"(ps.bestk[1]) : "memory"); tp2 = clock64(); }
         // per-window merge over the lanes, order (P desc, bin asc); a lane without a bin holds d = +inf -> P = 0, bin -1.
@@ -470,8 +488,8 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
                 fused_write_peak(out, (size_t)qwin[(gs + lane) % FZ_Q], km, Pm, K);
             }
             __syncwarp();
+            fused_retire(smem, gs, (unsigned)gc, lane);
             if (lane == 0) {
-                fused_retire(smem, gs, (unsigned)gc);
                 grp[slot].busy = 0;  // (results were read above; a new group may reuse the slot)
                 if (dbg_cta) dbg_cta[23] = clock64() - t_start;  // (the last group to finish writes last)
             }
@@ -632,9 +650,16 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             __syncwarp();  // makes lane 0's ring writes (claims during this window) visible to the next read
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = warp_sum(acc[i]);
+            unsigned seq = 0u;
+            if (lane == 0) seq = atomicAdd(&ctl->cov_seq, 1u);
+            seq = __shfl_sync(0xffffffffu, seq, 0);
+            for (;;) {  // queue slot free?
+                unsigned sd = 0u;
+                if (lane == 0) sd = ctl->scan_done;
+                if (seq - __shfl_sync(0xffffffffu, sd, 0) < (unsigned)FZ_Q) break;
+                __nanosleep(100);
+            }
             if (lane == 0) {
-                const unsigned seq = atomicAdd(&ctl->cov_seq, 1u);
-                while (seq - ctl->scan_done >= (unsigned)FZ_Q) __nanosleep(100);  // queue slot free?
                 const double dn = (double)N;
                 double *Rw = Rq + (size_t)(seq % FZ_Q) * 32;
                 Rw[0] = acc[0] / dn;   Rw[1] = 0.0;
@@ -734,33 +759,40 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
         asm volatile("griddepcontrol.wait;" ::: "memory");
 
         for (;;) {
-            if (st == 0) {
+            if (swarp == 0) {  // (the whole first scan warp, in uniform control flow; lane 0 decides)
                 // A pass streams the whole table from L2 once and costs ~27 k cycles whatever it holds, so it takes exactly
                 // FZ_WPT windows, and none is started once the launch is running out (see DRAIN in the file header).
                 unsigned start = 0, cnt = 0;
                 for (;;) {
-                    bool stop = false;
-                    fz_lock(ctl);
-                    start = ctl->claim;
-                    const unsigned avail = ctl->eig_done - start;
-                    const int fin = (int)ctl->cov_finished;
-                    if (ctl->mma_off) {
-                        stop = true;
-                    } else if (avail >= (unsigned)FZ_WPT && fin <= mma_fin_max) {
-                        cnt = FZ_WPT;
-                        ctl->claim = start + cnt;
-                    } else if ((ctl->tout && fin > mma_fin_max) || fin == FZ_COV_WARPS) {
-                        ctl->mma_off = 1u;
-                        stop = true;
+                    unsigned stop = 0u;
+                    fz_lock(ctl, lane);
+                    if (lane == 0) {
+                        start = ctl->claim;
+                        const unsigned avail = ctl->eig_done - start;
+                        const int fin = (int)ctl->cov_finished;
+                        if (ctl->mma_off) {
+                            stop = 1u;
+                        } else if (avail >= (unsigned)FZ_WPT && fin <= mma_fin_max) {
+                            cnt = FZ_WPT;
+                            ctl->claim = start + cnt;
+                        } else if ((ctl->tout && fin > mma_fin_max) || fin == FZ_COV_WARPS) {
+                            ctl->mma_off = 1u;
+                            stop = 1u;
+                        }
                     }
-                    fz_unlock(ctl);
+                    fz_unlock(ctl, lane);
+                    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+                    stop = __shfl_sync(0xffffffffu, stop, 0);
                     if (cnt || stop) break;
                     __nanosleep(200);
                 }
-                if (dbg && cnt == 0) dbg[blockIdx.x * FZ_TRACE + 16] = clock64() - t_start;  // when the tensor-core passes ended
-                ctl->batch_start = start;
-                ctl->batch_cnt = cnt;
-                __threadfence_block();
+                if (lane == 0) {
+                    if (dbg && cnt == 0) dbg[blockIdx.x * FZ_TRACE + 16] = clock64() - t_start;  // when the tensor-core passes ended
+                    ctl->batch_start = start;
+                    ctl->batch_cnt = cnt;
+                    __threadfence_block();
+                }
+                __syncwarp();
             }
             if (st < FZ_WPT) cand_cnt[st] = 0;
             bar_sync_scan();
@@ -1018,7 +1050,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             }
             if (dbg) scan_exact += clock64() - te0;
             bar_sync_scan();  // scratch and the queue slots may be reused from here on
-            if (st == 0) fused_retire(fz_smem, start, cnt);
+            if (swarp == 0) fused_retire(fz_smem, start, cnt, lane);
             scan_busy += clock64() - t0;
             ++scan_passes;
         }

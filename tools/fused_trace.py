@@ -39,5 +39,5 @@ print("  tensor-core passes ended %9.0f, windows taken by the fp64 drain workers
 print("  CTA done (all outputs written) %9.0f mean, %9.0f max; after the last covariance warp: %9.0f mean" % (tr[:, 18].mean(), tr[:, 18].max(), (tr[:, 18] - cov_end).mean()))
 print("  drain: %5.2f groups / CTA, unit busy cycles (sum over warps) %9.0f -> %7.0f per group-unit (%d units per group); last group finished %9.0f (%9.0f after the last covariance warp)" % (tr[:, 20].mean(), tr[:, 22].mean(), (tr[:, 22] / np.maximum(tr[:, 20] * 16, 1)).mean(), 16, tr[:, 23].mean(), (tr[:, 23] - cov_end).mean()))
 u = np.maximum(tr[:, 29], 1)
-print("  drain units: %5.1f / CTA; cycles per unit: first table row %7.0f, table sweep %7.0f, merge over lanes %7.0f, publish %7.0f; worker warps waiting for a unit: %9.0f cycles / CTA (sum over 16 warps)"
-      % (tr[:, 29].mean(), (tr[:, 24] / u).mean(), (tr[:, 25] / u).mean(), (tr[:, 26] / u).mean(), (tr[:, 27] / u).mean(), tr[:, 28].mean()))
+print("  drain units: %5.1f / CTA; cycles per unit: table sweep %7.0f, lane merge + publish %7.0f; units that found lane 0's warp split at the sweep %5.1f / at the merge %5.1f; worker warps waiting for a unit: %9.0f cycles / CTA (sum over 16 warps)"
+      % (tr[:, 29].mean(), (tr[:, 25] / u).mean(), (tr[:, 26] / u).mean(), tr[:, 24].mean(), tr[:, 27].mean(), tr[:, 28].mean()))
