@@ -420,8 +420,12 @@ def run_other_config(cid, args, torch, dist, dev, local, rank, G, peak_hbm, sm_m
     d_bins = torch.empty((W, n), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
 
+    d_all = torch.empty((G, W, n), dtype=torch.int32, device=dev) if G > 1 else None
+
     def step():
         blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(), stream=stream.cuda_stream)
+        if G > 1:  # BASELINE configs[3], [4]: "NCCL all-gather of peak indices" (gathered[r][i] <-> stream window i * G + r)
+            dist.all_gather_into_tensor(d_all.view(-1), d_bins.view(-1))
 
     for _ in range(2):
         step()
@@ -440,6 +444,9 @@ def run_other_config(cid, args, torch, dist, dev, local, rank, G, peak_hbm, sm_m
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    gathered_ok = None
+    if G > 1:  # every rank's bins arrived in every rank's buffer
+        gathered_ok = bool(torch.equal(d_all[rank], d_bins))
     # stage split of the same step (separate pass)
     blk.set_stage_timing(True)
     step()
@@ -474,6 +481,8 @@ def run_other_config(cid, args, torch, dist, dev, local, rank, G, peak_hbm, sm_m
            "stages_ms": {"cov": ms4[0], "eig": ms4[1], "scan": ms4[2], "topn": ms4[3], "chunks": chunks},
            "bins_checked": int(len(sel)), "bins_mismatch": mism, "bins_mismatch_last_replica": mism_last,
            "checker": "C oracle (port of work()) on the same bytes"}
+    if G > 1:
+        out["gather"] = {"how": "ncclAllGather of int32 bins per step inside the timed region", "own_shard_ok": gathered_ok}
     blk.close()
     del d_in, d_ang, d_lvl, d_bins
     torch.cuda.empty_cache()
@@ -484,6 +493,17 @@ def run_other_config(cid, args, torch, dist, dev, local, rank, G, peak_hbm, sm_m
 def run_ours(args):
     import torch
     import torch.distributed as dist
+
+    _t00 = time.perf_counter()
+
+    def leg(msg):  # progress of the legs on stderr (BENCH_VERBOSE=1); BENCH_WATCHDOG=<s> dumps every thread's stack every <s> seconds
+        if os.environ.get("BENCH_VERBOSE"):
+            print("[bench rank %s +%.1fs] %s" % (os.environ.get("RANK", "0"), time.perf_counter() - _t00, msg), file=sys.stderr, flush=True)
+
+    if os.environ.get("BENCH_WATCHDOG"):
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
 
     from gr_baz_b200.music_doa import music_doa
 
@@ -559,6 +579,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    leg('setup done, warm-up')
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
@@ -575,6 +596,7 @@ def run_ours(args):
     drain()  # the timed region ends when every rank holds every step's gathered bins
     e1.record(stream)
     sync_all()
+    leg('timed region done')
     ms = e0.elapsed_time(e1)
     launches = blk.launch_count() - l0
     clocks = sampler.stop() if sampler else None
@@ -587,6 +609,7 @@ def run_ours(args):
         launches = int(lt.item())
     value = W * G * args.steps / (ms * 1e-3)
 
+    leg('gather check')
     # the gathered bins against the collective they replace (outside the timed region)
     gather_check = None
     last_bins = d_bins2[(stepno[0] - 1) & 1 if (G > 1 and not fused_gather) else 0]
@@ -619,9 +642,26 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
 
+    leg('roofline leg')
     # ---- roofline leg: stage timing of the same step (separate, untimed passes) -------------
     roof = None
     stages = None
+    fused = cfg["m"] == 4 and n == 1 and os.environ.get("MUSIC_B200_FUSED", "1") != "0"
+    b2b_ms = None
+    if fused and G > 1:
+        # back-to-back launches of the dominant kernel alone (no gather wait in the timed region).  EVERY rank runs
+        # them: the fused all-gather counts calls per rank (epochs), a rank that made extra calls would wait forever
+        # for peers that did not.
+        for _ in range(3):
+            blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(), stream=stream.cuda_stream)
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        r0.record(stream)
+        for _ in range(args.steps):
+            blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(), stream=stream.cuda_stream)
+        r1.record(stream)
+        sync_all()
+        b2b_ms = r0.elapsed_time(r1) / args.steps
     if rank == 0:
         def time_stages(b, reps=5):
             b.set_stage_timing(True)
@@ -633,7 +673,6 @@ def run_ours(args):
             b.set_stage_timing(False)
             return [m / reps for m in ms4], chunks // reps
 
-        fused = cfg["m"] == 4 and n == 1 and os.environ.get("MUSIC_B200_FUSED", "1") != "0"
         # the three stages timed separately on a second handle that runs the unfused kernels
         old_env = os.environ.get("MUSIC_B200_FUSED")
         os.environ["MUSIC_B200_FUSED"] = "0"
@@ -648,19 +687,8 @@ def run_ours(args):
         s4, nl = time_stages(blk3)
         blk3.close()
         if fused:
-            # a single-GPU pass of nothing but back-to-back launches of this kernel, CUDA events on its stream
-            for _ in range(3):
-                blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(), stream=stream.cuda_stream)
-            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            r0.record(stream)
-            for _ in range(args.steps):
-                blk.process_device(d_in.data_ptr(), W, d_ang.data_ptr(), d_lvl.data_ptr(), None, d_bins.data_ptr(), stream=stream.cuda_stream)
-            r1.record(stream)
-            torch.cuda.synchronize()
-            dom_ms = r0.elapsed_time(r1) / args.steps
-            if G == 1:
-                dom_ms = ms / args.steps  # the timed region itself holds nothing but these launches
+            # nothing but back-to-back launches of this kernel, CUDA events on its stream: at N = 1 the timed region itself
+            dom_ms = ms / args.steps if G == 1 else b2b_ms
             dom_how = "CUDA events around %d back-to-back launches on the launch stream (the step is this one kernel)" % args.steps
             kernel = "music4_fused_kernel (K1 covariance + K2 eigenvectors + K3 scan in one persistent launch)"
         else:
@@ -688,6 +716,7 @@ def run_ours(args):
                 "unfused_cov_kernel_frac": bytes_per_window(cfg) * W / (s4[0] * 1e-3) / 1e9 / peak}
 
     # ---- e2e: block API with HOST buffers (H2D + D2H inside the timed region) --------------------------------------
+    leg('e2e leg')
     e2e = None
     if not args.no_e2e:
         We = W
@@ -747,6 +776,7 @@ def run_ours(args):
         del h_in
         # N > 1: ONE block over all N GPUs, one work() call per step, driven by rank 0 alone
         if G > 1:
+            leg('e2e: single block over all GPUs')
             dist.barrier()
             single = None
             if rank == 0:
@@ -773,11 +803,10 @@ def run_ours(args):
                 del hm
             dist.barrier()
             if rank == 0:
+                # headline e2e at N GPUs: one block per GPU, each fed by its own host process (the launch the driver makes);
+                # the ONE-block-over-all-GPUs form (one host thread, one buffer) is reported beside it
                 e2e["per_rank_blocks_value"] = per_rank_value
                 e2e["single_block_all_gpus"] = single
-                e2e["value"] = single["value"]
-                e2e["api"] = single["api"] + "; per_rank_blocks_value = N processes with one block each"
-                e2e["e2e_input_gbs"] = single["input_gbs"]
 
     # ---- SURVEY 8(f) rows built so far, same workload (untimed w.r.t. the headline; rank 0, N = 1) ----------
     next_rows = None
@@ -830,6 +859,7 @@ def run_ours(args):
                                "guarded_entries": guarded, "table_bit_identical": same,
                                "api": "music_b200_set_geometry vs calculate_antenna_array_response + set_array_response"}
 
+    leg('other configs')
     # ---- BASELINE configs[2..4] ---------------------------------------------------------------------------------
     other = None
     if not args.no_other_configs and args.config == 2:
