@@ -339,7 +339,7 @@ __device__ __forceinline__ void fused_retire(unsigned char *smem, const unsigned
 // + lane, i = 0, 1, ..), the next row is requested before the current one is evaluated.  Returns the number of units
 // this warp processed.
 template <bool TRACE>
-__device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float *__restrict__ tab_c64, const unsigned idle_ns, const int nch, const int K,
+__device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float *__restrict__ tab_c64, const unsigned idle_ns, const int nch, const int early_drain, const int K,
                                                const PeakOut out, long long *__restrict__ dbg_in, const long long t_start)
 {
     long long *const dbg_cta = TRACE ? dbg_in : nullptr;
@@ -366,7 +366,7 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
                 const int cur = ctl->dg_open;
                 if (cur >= 0 && grp[cur].next_chunk < (unsigned)nch) {
                     slot = cur; chunk = (int)grp[cur].next_chunk++; gs = grp[cur].gs; gc = grp[cur].gc;
-                } else if (ctl->mma_off) {
+                } else if (ctl->mma_off || (early_drain && ctl->tout)) {
                     const unsigned start = ctl->claim, avail = ctl->eig_done - start;
                     // every window of this CTA has its eigenvectors: what is left may go out as a partial group
                     const bool last = ctl->cov_finished == (unsigned)FZ_COV_WARPS &&
@@ -479,6 +479,7 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
             }
         }
         last = __shfl_sync(0xffffffffu, last, 0);
+        __syncwarp();  // (memory ordering for the lanes that read the other units' results below)
         if (last) {
             // this warp finished the group's last unit: merge the chunks (lane b <-> window b; any order gives the same
             // result, (P desc, bin asc) is a total order)
@@ -520,7 +521,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     const GatherFlags gather_flags /* epoch flags of the fused bins all-gather (out.npeer > 0) */,
                     const int mma_fin_max /* no tensor-core pass starts once the window tickets have run out and this many covariance warps are done (0: once the tickets have run out); < 0: never any */,
                     const unsigned idle_ns /* sleep of a drain worker that found no unit */,
-                    const int nch /* drain units per group, 1..FZ_NCH */)
+                    const int nch /* drain units per group, 1..FZ_NCH */,
+                    const int early_drain /* finished covariance warps start draining as soon as the tickets have run out, beside the tensor-core passes */)
 {
     long long *const dbg = TRACE ? dbg_in : nullptr;
     // programmatic dependent launch: the next launch on this stream may take the SMs this grid leaves (it needs a whole
@@ -697,7 +699,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             if (dbg && fin == 0) dbg[blockIdx.x * FZ_TRACE + 1] = clock64() - t_start;                           // first one
         }
         __syncwarp();
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0, eig_jacobi = 0;
@@ -741,7 +743,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 10] = eig_rounds;
             dbg[blockIdx.x * FZ_TRACE + 19] = eig_jacobi;
         }
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else {
         // ================= scan warps =================
         const int st = threadIdx.x - 32 * (FZ_COV_WARPS + 1);  // 0..223
@@ -1077,7 +1079,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 3] = (long long)(g_end - g_start);   // ns, this CTA's lifetime (overwrites covariance warp 3's slot)
             dbg[blockIdx.x * FZ_TRACE + 2] = (long long)g_start;             // ns, absolute start (overwrites covariance warp 2's slot)
         }
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     }
     // The last CTA to finish re-arms the ticket counter for the next launch (launches of one handle are
     // serialised by the host, and by now every covariance warp has drawn a ticket >= W).
