@@ -767,18 +767,22 @@ constexpr int EIGC_WARPS = 4;
 
 // One warp, one window: A (M x M complex, row-major, shared memory) holds R on entry and the rotated matrix (its diagonal =
 // the eigenvalues) on exit, V (M x M scratch) the eigenvectors as columns; rot / pair: M/2 entries of warp-private scratch.
-template <int M>
+// P = row pitch of A and V in complex entries.  P = M + 1 with the column phase running row-fastest over the lanes makes a
+// quarter warp (8 lanes, one 128-bit wavefront) touch 8 different rows of ONE column: chunk (k P + p) mod 8 = (k + p) mod 8,
+// all distinct - no bank conflicts; with P = M and pair-fastest lanes the 8 columns of one row collide pairwise
+// (c and c + 8 share banks): 56.6 M conflicts per 4096 windows at M = 16 (profiles/r02_ncu_config5_kernels.txt).
+template <int M, int P = M>
 __device__ __forceinline__ void eig_coop_warp(double2 *A, double2 *V, double (*rot)[4], int (*pair)[2], const int lane)
 {
     static_assert(M % 2 == 0 && M <= MAXM, "even M only");
     constexpr int H = M / 2;
-    for (int i = lane; i < M * M; i += 32) V[i] = make_double2((i / M == i % M) ? 1.0 : 0.0, 0.0);
+    for (int i = lane; i < M * M; i += 32) V[(i / M) * P + i % M] = make_double2((i / M == i % M) ? 1.0 : 0.0, 0.0);
     __syncwarp();
     double prev_off = 1e300;
     for (int sweep = 0; sweep < 60; ++sweep) {
         double off = 0.0, fro = 0.0;
         for (int i = lane; i < M * M; i += 32) {
-            const double2 a = A[i];
+            const double2 a = A[(i / M) * P + i % M];
             const double e2 = a.x * a.x + a.y * a.y;
             fro += e2;
             if (i / M != i % M) off += e2;
@@ -795,8 +799,8 @@ __device__ __forceinline__ void eig_coop_warp(double2 *A, double2 *V, double (*r
                 if (lane == 0) { p = M - 1; q = step; }
                 else { p = (step + lane) % (M - 1); q = (step - lane + (M - 1)) % (M - 1); }
                 if (p > q) { const int t = p; p = q; q = t; }
-                const double2 g2 = A[p * M + q];
-                const double app = A[p * M + p].x, aqq = A[q * M + q].x;
+                const double2 g2 = A[p * P + q];
+                const double app = A[p * P + p].x, aqq = A[q * P + q].x;
                 const double gg = fma(g2.x, g2.x, g2.y * g2.y);
                 const bool nz = gg > 0.0;
                 const double rg = nz ? rsqrt(gg) : 0.0;
@@ -818,18 +822,18 @@ __device__ __forceinline__ void eig_coop_warp(double2 *A, double2 *V, double (*r
             __syncwarp();
             // columns: B[k][p] = c A[k][p] - conj(sw) A[k][q],  B[k][q] = sw A[k][p] + c A[k][q]   (A and V)
             for (int it = lane; it < M * H; it += 32) {
-                const int k = it / H, i = it % H;
+                const int k = (P == M) ? it / H : it % M, i = (P == M) ? it % H : it / M;
                 const int p = pair[i][0], q = pair[i][1];
                 const double c = rot[i][0], swr = rot[i][1], swi = rot[i][2];
                 {
-                    const double2 ap = A[k * M + p], aq = A[k * M + q];
-                    A[k * M + p] = make_double2(c * ap.x - (swr * aq.x + swi * aq.y), c * ap.y - (swr * aq.y - swi * aq.x));
-                    A[k * M + q] = make_double2(c * aq.x + (swr * ap.x - swi * ap.y), c * aq.y + (swr * ap.y + swi * ap.x));
+                    const double2 ap = A[k * P + p], aq = A[k * P + q];
+                    A[k * P + p] = make_double2(c * ap.x - (swr * aq.x + swi * aq.y), c * ap.y - (swr * aq.y - swi * aq.x));
+                    A[k * P + q] = make_double2(c * aq.x + (swr * ap.x - swi * ap.y), c * aq.y + (swr * ap.y + swi * ap.x));
                 }
                 {
-                    const double2 vp = V[k * M + p], vq = V[k * M + q];
-                    V[k * M + p] = make_double2(c * vp.x - (swr * vq.x + swi * vq.y), c * vp.y - (swr * vq.y - swi * vq.x));
-                    V[k * M + q] = make_double2(c * vq.x + (swr * vp.x - swi * vp.y), c * vq.y + (swr * vp.y + swi * vp.x));
+                    const double2 vp = V[k * P + p], vq = V[k * P + q];
+                    V[k * P + p] = make_double2(c * vp.x - (swr * vq.x + swi * vq.y), c * vp.y - (swr * vq.y - swi * vq.x));
+                    V[k * P + q] = make_double2(c * vq.x + (swr * vp.x - swi * vp.y), c * vq.y + (swr * vp.y + swi * vp.x));
                 }
             }
             __syncwarp();
@@ -839,17 +843,17 @@ __device__ __forceinline__ void eig_coop_warp(double2 *A, double2 *V, double (*r
                 const int i = it / M, k = it % M;
                 const int p = pair[i][0], q = pair[i][1];
                 const double c = rot[i][0], swr = rot[i][1], swi = rot[i][2];
-                const double2 bp = A[p * M + k], bq = A[q * M + k];
-                A[p * M + k] = make_double2(c * bp.x - (swr * bq.x - swi * bq.y), c * bp.y - (swr * bq.y + swi * bq.x));
-                A[q * M + k] = make_double2(c * bq.x + (swr * bp.x + swi * bp.y), c * bq.y + (swr * bp.y - swi * bp.x));
+                const double2 bp = A[p * P + k], bq = A[q * P + k];
+                A[p * P + k] = make_double2(c * bp.x - (swr * bq.x - swi * bq.y), c * bp.y - (swr * bq.y + swi * bq.x));
+                A[q * P + k] = make_double2(c * bq.x + (swr * bp.x + swi * bp.y), c * bq.y + (swr * bp.y - swi * bp.x));
             }
             __syncwarp();
             if (lane < H) {  // exact zeros / real diagonal where the rotation says so
                 const int p = pair[lane][0], q = pair[lane][1];
-                A[p * M + q] = make_double2(0.0, 0.0);
-                A[q * M + p] = make_double2(0.0, 0.0);
-                A[p * M + p].y = 0.0;
-                A[q * M + q].y = 0.0;
+                A[p * P + q] = make_double2(0.0, 0.0);
+                A[q * P + p] = make_double2(0.0, 0.0);
+                A[p * P + p].y = 0.0;
+                A[q * P + q].y = 0.0;
             }
             __syncwarp();
         }
@@ -858,17 +862,17 @@ __device__ __forceinline__ void eig_coop_warp(double2 *A, double2 *V, double (*r
 
 // ascending, stable ranks; eigenvector j -> vw[rank(j)][.] (component i), phase fixed so that component 0 is real;
 // ew (may be null): the eigenvalues in the same order
-template <int M>
+template <int M, int P = M>
 __device__ __forceinline__ void eig_coop_store(const double2 *A, const double2 *V, double *ew, double2 *vw, const int lane)
 {
     for (int it = lane; it < M * M; it += 32) {
         const int j = it / M, i = it % M;  // column j, component i
-        const double wj = A[j * M + j].x;
+        const double wj = A[j * P + j].x;
         int rank = 0;
-        for (int l = 0; l < M; ++l) rank += eig_before(A[l * M + l].x, l, wj, j);
+        for (int l = 0; l < M; ++l) rank += eig_before(A[l * P + l].x, l, wj, j);
         double pr, pi;
-        eig_phase(V[0 * M + j].x, V[0 * M + j].y, pr, pi);
-        const double2 v = V[i * M + j];
+        eig_phase(V[0 * P + j].x, V[0 * P + j].y, pr, pi);
+        const double2 v = V[i * P + j];
         vw[rank * M + i] = make_double2(v.x * pr - v.y * pi, i == 0 ? 0.0 : v.x * pi + v.y * pr);
         if (i == 0 && ew) ew[rank] = wj;
     }
@@ -879,8 +883,9 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
                                                                    double *__restrict__ Vt, int W)
 {
     constexpr int H = M / 2;
-    __shared__ double2 sA[EIGC_WARPS][M * M];
-    __shared__ double2 sV[EIGC_WARPS][M * M];
+    constexpr int P = (M == 16) ? M + 1 : M;  // padded pitch where a row spans more than the 32 banks (see eig_coop_warp)
+    __shared__ double2 sA[EIGC_WARPS][M * P];
+    __shared__ double2 sV[EIGC_WARPS][M * P];
     __shared__ double sRot[EIGC_WARPS][H][4];  // c, Re(s w), Im(s w), unused
     __shared__ int sPair[EIGC_WARPS][H][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -888,9 +893,9 @@ __global__ void __launch_bounds__(EIGC_WARPS * 32) eig_coop_kernel(const double 
     if (w >= W) return;
     double2 *A = sA[warp], *V = sV[warp];
     const double2 *Rw = reinterpret_cast<const double2 *>(R) + (size_t)w * M * M;
-    for (int i = lane; i < M * M; i += 32) A[i] = Rw[i];
-    eig_coop_warp<M>(A, V, sRot[warp], sPair[warp], lane);
-    eig_coop_store<M>(A, V, evals + (size_t)w * M, reinterpret_cast<double2 *>(Vt) + (size_t)w * M * M, lane);
+    for (int i = lane; i < M * M; i += 32) A[(i / M) * P + i % M] = Rw[i];
+    eig_coop_warp<M, P>(A, V, sRot[warp], sPair[warp], lane);
+    eig_coop_store<M, P>(A, V, evals + (size_t)w * M, reinterpret_cast<double2 *>(Vt) + (size_t)w * M * M, lane);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small invocations of the kernels compute-sanitizer should look at: run as
   compute-sanitizer --tool racecheck|memcheck|synccheck python tools/sanitize_targets.py <target>
-targets: fused (C1-size windows, 2000 of them + a ragged 1187 + a drain-only 9), fused_jacobi, covn8, covn16, eig16, multi"""
+targets: fused (C1-size windows, 2000 of them + a ragged 1187 + a drain-only 9), fused_jacobi, fused8, covn8, covn16, eig16, multi"""
 import os
 import sys
 
@@ -36,7 +36,9 @@ if target in ("fused", "fused_jacobi"):
     if target == "fused_jacobi":
         os.environ["MUSIC_B200_EIG"] = "jacobi"
     run(synth.config(1), (2000, 1187, 9))
-elif target == "covn8":
+elif target in ("covn8", "fused8"):  # M = 8, n = 1 takes the fused M = 8 kernel by default; covn8 = the three-kernel path
+    if target == "covn8":
+        os.environ["MUSIC_B200_FUSED"] = "0"
     run(synth.config(4, snapshots=1024, resolution=360), (600, 37))
 elif target == "covn16":
     run(synth.config(5, snapshots=512, resolution=360), (300, 19))

@@ -83,26 +83,33 @@ def summarize(rep, out_name, title):
     return traffic
 
 
-t1 = summarize(os.path.join(src, "prof_fused.ncu-rep"), "%s_ncu_fused_kernel.txt" % rnd,
-               "music4_fused_kernel (default path for M=4, n=1): BASELINE config 2, 10 000 windows per launch")
+commit = None
+if os.path.exists(os.path.join(src, "commit.txt")):
+    commit = open(os.path.join(src, "commit.txt")).read().strip()
+t1 = summarize(os.path.join(src, "prof_fused4.ncu-rep" if os.path.exists(os.path.join(src, "prof_fused4.ncu-rep")) else "prof_fused.ncu-rep"),
+               "%s_ncu_fused_kernel.txt" % rnd, "music4_fused_kernel (default path for M=4, n=1): BASELINE config 2, 10 000 windows per launch")
 t2 = summarize(os.path.join(src, "prof.ncu-rep"), "%s_ncu_unfused_kernels.txt" % rnd,
                "unfused three-kernel path (MUSIC_B200_FUSED=0): cov4_tma_kernel, eig_kernel, scan_peak1_kernel")
+t8 = summarize(os.path.join(src, "prof_fused8.ncu-rep"), "%s_ncu_fused8_kernel.txt" % rnd,
+               "music8_fused_kernel (default path for M=8, n=1): BASELINE config 4 shape, 8192 windows per launch")
 t4 = summarize(os.path.join(src, "prof_covn_c4.ncu-rep"), "%s_ncu_covN_M8.txt" % rnd,
                "covN_tma_kernel<8> (K1 for M = 8): BASELINE config 4 shape, 8192 windows per launch")
-t5 = summarize(os.path.join(src, "prof_covn_c5.ncu-rep"), "%s_ncu_covN_M16.txt" % rnd,
-               "covN_tma_kernel<16> (K1 for M = 16): BASELINE config 5 shape, 4096 windows per launch")
+t5 = summarize(os.path.join(src, "prof_c5.ncu-rep" if os.path.exists(os.path.join(src, "prof_c5.ncu-rep")) else "prof_covn_c5.ncu-rep"),
+               "%s_ncu_config5_kernels.txt" % rnd, "covN_tma_kernel<16> and eig_coop_kernel<16> (M = 16): BASELINE config 5 shape")
 for f, name in (("bench_c3.json", "%s_bench_config3.json" % rnd), ("bench_c4.json", "%s_bench_config4.json" % rnd),
                 ("bench_c5.json", "%s_bench_config5.json" % rnd), ("launches.csv", "%s_launches.csv" % rnd), ("microbench.log", "%s_microbench.txt" % rnd),
                 ("bench.json", "%s_bench_1gpu.json" % rnd), ("bench_ref.json", "%s_bench_reference_arm.json" % rnd),
                 ("bench_MUSIC_B200_FUSED_0.json", "%s_bench_unfused.json" % rnd), ("pytest_gpu.log", "%s_pytest_gpu.txt" % rnd),
-                ("gpu.txt", "%s_gpu.txt" % rnd), ("fused_trace.txt", "%s_fused_trace.txt" % rnd)):
+                ("gpu.txt", "%s_gpu.txt" % rnd), ("fused_trace.txt", "%s_fused_trace.txt" % rnd), ("smoke.log", "%s_smoke.txt" % rnd)):
     if os.path.exists(os.path.join(src, f)):
         shutil.copy(os.path.join(src, f), os.path.join(dst, name))
 if t1:
     tr = {"config2": next(iter(t1.values())), "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-          "kernel": next(iter(t1.keys())), "capture": "%s_ncu_fused_kernel.txt" % rnd}
-    for key, t in (("config4", t4), ("config5", t5)):
-        if t:
-            tr[key] = next(iter(t.values()))
+          "kernel": next(iter(t1.keys())), "capture": "%s_ncu_fused_kernel.txt" % rnd, "capture_commit": commit}
+    if t8:
+        tr["config4"] = next(iter(t8.values()))
+        tr["config4_kernel"] = next(iter(t8.keys()))
+    if t5:
+        tr["config5_kernels"] = t5
     json.dump(tr, open(os.path.join(dst, "roofline_traffic.json"), "w"), indent=1)
 print(os.listdir(dst))
