@@ -248,11 +248,35 @@ class CpuArm:
             p.join(timeout=5)
 
 
-def host_threads():
+def cgroup_cpu_quota():
+    """CPUs this container may use according to its cgroup (v2 cpu.max or v1 cfs quota), or None if unlimited / unknown."""
     try:
-        return len(os.sched_getaffinity(0))
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            return float(q) / float(per)
     except Exception:
-        return os.cpu_count() or 1
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and per > 0:
+            return q / per
+    except Exception:
+        pass
+    return None
+
+
+def host_threads():
+    """Worker processes of the CPU arm: the CPUs this process may run on, capped by the container's CPU quota (an affinity
+    mask of 128 under a 10-CPU quota would only oversubscribe the quota and report a core count the arm never had)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    q = cgroup_cpu_quota()
+    if q:
+        n = max(1, min(n, int(q + 0.999)))
+    return n
 
 
 def one_core_rate(cfg, table_c64, seed):
@@ -345,7 +369,8 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(cfg, args.config, W, args.gpus),
         "cpu_baseline": {"value": value, "unit": "windows/s", "cores": procs, "kind": "port", "sample": sample,
-                         "value_1core": r1, "parallel_efficiency": value / (r1 * procs)},
+                         "value_1core": r1, "parallel_efficiency": value / (r1 * procs), "effective_cores": value / r1,
+                         "cgroup_cpu_quota": cgroup_cpu_quota()},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "reference_source": reference_source_rate(cfg, table, seed, procs),
     }
@@ -886,6 +911,9 @@ def run_ours(args):
                "sample": "%d windows (%d worker processes x %d windows of the same synthetic stream x %d passes), %.2f s wall, C port of work() (-O3 -DNDEBUG)"
                          % (r["windows"], procs, r["per_proc"], r["reps"], r["seconds"]),
                "value_1core": r["value_1core"], "parallel_efficiency": r["parallel_efficiency"],
+               "effective_cores": r["value"] / r["value_1core"], "cgroup_cpu_quota": cgroup_cpu_quota(),
+               "note": "effective_cores = value / value_1core: what the box actually gave the arm (affinity masks on shared hosts "
+                       "list more CPUs than the container's share; the arm cannot go faster than that share)",
                "slowest_worker_s": r["slowest_worker_s"], "fastest_worker_s": r["fastest_worker_s"]}
 
     if rank == 0:
