@@ -78,6 +78,7 @@ struct music_b200 {
     bool pipeline = false;   // MUSIC_B200_PIPE=1 enables the sub-batch pipeline (launch-bound at 10k windows: off)
     unsigned *work_ctr = nullptr;      // persistent kernels: ring of self-resetting (window tickets, finished CTAs) pairs, CTR_RING per slot
     unsigned ctr_seq[2] = {0, 0};      // next ring entry per slot
+    bool fused_spec = true;            // the spectrum port on the fused M = 4 kernel (MUSIC_B200_FUSED_SPEC=0: three-kernel path)
     int early_drain = 0;               // fused kernel: drain beside the last tensor-core passes (MUSIC_B200_EARLY_DRAIN)
     int drain_nch = 16;                // fused kernel: drain units per group (MUSIC_B200_DRAIN_NCH, 1..32)
     unsigned idle_ns = 100;            // fused kernel: sleep of an idle drain worker (MUSIC_B200_IDLE_NS)
@@ -549,7 +550,7 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         for (uint32_t r = 0; r < h->m; ++r) planar_fusable = planar_fusable && (reinterpret_cast<uintptr_t>(planar->p[r]) & 15u) == 0;
     }
     const bool local_peaks = h->peak_mode == MUSIC_B200_PEAKS_LOCAL_MAXIMA;
-    if ((!planar || planar_fusable) && h->fused && !local_peaks && h->m == 4 && h->n == 1 && !d_spec && !d_P64 && !d_R && !d_ev) {
+    if ((!planar || planar_fusable) && h->fused && !local_peaks && h->m == 4 && h->n == 1 && (!d_spec || h->fused_spec) && !d_P64 && !d_R && !d_ev) {
         // whole call in one persistent launch (music_fused.cuh); no workspace involved
         cudaEvent_t *tev = timing_events(h);
         if (tev) cudaEventRecord(tev[0], st);
@@ -576,11 +577,11 @@ int enqueue_device(music_b200 *h, const float *d_in, uint32_t nwindows, float *d
         if (planar) {
             auto kern = tr ? music4_fused_kernel<true, true> : music4_fused_kernel<true, false>;
             le = cudaLaunchKernelEx(&lc, kern, (const float *)nullptr, *planar, 0ull, (unsigned)hop, fz, c64, na_max, W_i, N_i, K_i, po, ctr,
-                                    h->fused_trace, h->eig_mode, gf, h->mma_fin_max, h->idle_ns, h->drain_nch, h->early_drain);
+                                    h->fused_trace, h->eig_mode, gf, h->mma_fin_max, h->idle_ns, h->drain_nch, h->early_drain, d_spec);
         } else {
             auto kern = tr ? music4_fused_kernel<false, true> : music4_fused_kernel<false, false>;
             le = cudaLaunchKernelEx(&lc, kern, d_in, PlanarStreams{}, 0ull, 0u, fz, c64, na_max, W_i, N_i, K_i, po, ctr, h->fused_trace,
-                                    h->eig_mode, gf, h->mma_fin_max, h->idle_ns, h->drain_nch, h->early_drain);
+                                    h->eig_mode, gf, h->mma_fin_max, h->idle_ns, h->drain_nch, h->early_drain, d_spec);
         }
         CU(h, le);
         h->launches++;
@@ -931,6 +932,7 @@ int music_b200_create(music_b200 **out, uint32_t m, uint32_t n, uint32_t nsample
         if (const char *e = getenv("MUSIC_B200_EIG")) h->eig_mode = !strcmp(e, "jacobi") ? 1 : !strcmp(e, "jacobi1") ? 2 : 0;
         if (const char *e = getenv("MUSIC_B200_PDL")) h->pdl = atoi(e) != 0;
         if (const char *e = getenv("MUSIC_B200_DRAIN_NCH")) h->drain_nch = std::max(1, std::min((int)FZ_NCH, atoi(e)));
+        if (const char *e = getenv("MUSIC_B200_FUSED_SPEC")) h->fused_spec = atoi(e) != 0;
         if (const char *e = getenv("MUSIC_B200_EARLY_DRAIN")) h->early_drain = atoi(e) != 0;
         if (const char *e = getenv("MUSIC_B200_IDLE_NS")) h->idle_ns = (unsigned)std::max(0, atoi(e));
         if (const char *e = getenv("MUSIC_B200_MMA_FIN")) h->mma_fin_max = std::max(-1, std::min(8, atoi(e)));

@@ -22,15 +22,19 @@
 //                     Typically 2-60 bins per window; if more than FZ_CMAX bins of a window survive (flat
 //                     spectra, e.g. an all-zero window) every bin of that window is evaluated in fp64 instead.
 //                The result is therefore bit-identical to an all-fp64 scan.
-//   DRAIN        A tensor-core pass has a latency of ~27 k cycles whatever it holds, and that latency (plus the
+//   DRAIN        A tensor-core pass has a latency of ~35 k cycles whatever it holds, and that latency (plus the
 //                eigensolver's) used to be the tail of the launch: 58 k cycles per CTA with HBM idle.  Once the
-//                window tickets have run out and more than FZ_MMA_FIN covariance warps are done, no new pass is
-//                started: every warp that has nothing left to do - covariance warps as they finish, the scan warps
-//                after their last pass, the eigenvector warp at the end - becomes a drain worker and takes
-//                (group of <= 4 windows, 1/8 of the bins) units of an all-fp64 scan (scan_bin, the unfused
-//                scan_peak1_kernel's hot loop; the FP64 pipe is free by then), merged per group in fixed order by
-//                the warp that finishes the group's last unit.  Same formula, same tie rule: bit-identical to the
-//                tensor-core path, at ~1.2 k cycles per window instead of a 27 k-cycle pass.
+//                window tickets have run out and `mma_fin_max` covariance warps are done, no new pass is started:
+//                every warp that has nothing left to do - covariance warps as they finish, the scan warps after
+//                their last pass, the eigenvector warp at the end - becomes a drain worker and takes (group of 4
+//                windows - fewer only for the CTA's very last ones -, 1/nch of the bins, interleaved in steps of 32)
+//                units of an all-fp64 scan (drain_bin = scan_bin's arithmetic from the unfused scan_peak1_kernel; the
+//                FP64 pipe is free by then), merged per group by the warp that finishes the group's last unit.  Same
+//                formula, same tie rule: bit-identical to the tensor-core path, at ~4 k cycles of the whole SM per
+//                window instead of a 35 k-cycle pass.  With the spectrum port connected every window goes this way.
+//   LAUNCH       programmatic dependent launch: the next launch's CTAs take over each SM as this one leaves it
+//                (griddepcontrol.launch_dependents at the start; every writer waits with griddepcontrol.wait before
+//                its first output so that results land in stream order); per-launch ticket counters.
 //
 // Screen error bound.  a is stored in fp32 exactly (the block's table IS complex64) and split at run
 // time by truncation: a_hi = a & ~0x1fff (|a - a_hi| < 2^-10|a|), a_lo = (a - a_hi) & ~0x1fff (the
@@ -50,8 +54,8 @@
 // table sweeps of a pass are one loop body, merges are rolled loops, and the clock64 trace exists only in the TRACE
 // instantiation of the kernel.
 //
-// Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does per
-// window except the optional spectrum port).
+// Reference lines covered: /root/reference/lib/baz_music_doa.cc:74-155 (everything work() does per window; with the
+// optional spectrum port connected, :120-121, every window takes the fp64 drain workers, which also write (float)P[k]).
 #pragma once
 #include "music_kernels.cuh"
 #include "music_eig4p.cuh"
@@ -229,9 +233,13 @@ __device__ __noinline__ void fused_jacobi4(const double *Rw, double *vw, const b
 
 // One steering-table row against FZ_DG windows: scan_bin's hot path (music_kernels.cuh) with the rare exact evaluation
 // out of line.  Same arithmetic, same decisions: bit-identical results.
+// SPEC = true (the spectrum port is connected, /root/reference/lib/baz_music_doa.cc:120-121): every (bin, window) strength
+// is needed, so each d is made exact (direct form inside the cancellation guard), P = 1 / d goes to spec_row[b][k] as float
+// and the peak is kept on the strengths themselves (strict '>', :132); bestP = the running maxima.
+template <bool SPEC>
 __device__ __forceinline__ void drain_bin(const double (&ar)[4], const double (&ai)[4], const double na, const int k,
                                           const uint32_t (&ev)[4], PeakState<4> &ps, const float *__restrict__ tab_c64,
-                                          const uint64_t pol_keep)
+                                          const uint64_t pol_keep, double (&bestP)[4], float *const (&spec_row)[4], const int gc)
 {
     constexpr int sig = 16 * 3 * 4;  // byte offset of the signal vector (largest eigenvalue)
     double cr[4], ci[4];
@@ -254,6 +262,17 @@ __device__ __forceinline__ void drain_bin(const double (&ar)[4], const double (&
         }
     }
     const int hg = __double2hiint(COMPLEMENT_GUARD * na);
+    if (SPEC) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            double d = fma(-cr[b], cr[b], fma(-ci[b], ci[b], na));
+            if (!(__double2hiint(d) > hg)) d = fused_exact_d(tab_c64, k, ev[b], pol_keep);  // inside the guard, negative or NaN
+            const double P = fused_recip(d);
+            if (b < gc) spec_row[b][k] = (float)P;
+            if (P > bestP[b]) { bestP[b] = P; ps.bestd[b] = d; ps.bestk[b] = k; }
+        }
+        return;
+    }
     unsigned cold = 0;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -340,7 +359,7 @@ __device__ __forceinline__ void fused_retire(unsigned char *smem, const unsigned
 // this warp processed.
 template <bool TRACE>
 __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float *__restrict__ tab_c64, const unsigned idle_ns, const int nch, const int early_drain, const int K,
-                                               const PeakOut out, long long *__restrict__ dbg_in, const long long t_start)
+                                               float *__restrict__ spec /* [W][K] or null */, const PeakOut out, long long *__restrict__ dbg_in, const long long t_start)
 {
     long long *const dbg_cta = TRACE ? dbg_in : nullptr;
     FusedCtl *ctl = reinterpret_cast<FusedCtl *>(smem + FZ_OFF_CTL);
@@ -433,15 +452,32 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
         int k = chunk * 32 + lane;
         if (TRACE && dbg_cta && __activemask() != 0xffffffffu) ++ndiv0;  // (trace: is the warp converged at the sweep?)
         if (k < K) load_row(k, ar, ai, na);
-#pragma unroll 1
-        while (k < K) {
-            const int kn = k + nch * 32;
-            if (kn < K) load_row(kn, nr, ni, nna);
-            drain_bin(ar, ai, na, k, ev, ps, tab_c64, pol_keep);
+        double bestP[FZ_DG] = {0.0, 0.0, 0.0, 0.0};
+        float *spec_row[FZ_DG];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { ar[i] = nr[i]; ai[i] = ni[i]; }
-            na = nna;
-            k = kn;
+        for (int b = 0; b < FZ_DG; ++b) spec_row[b] = spec ? spec + (size_t)qwin[(gs + (unsigned)min(b, gc - 1)) % FZ_Q] * K : nullptr;
+        if (spec) {
+#pragma unroll 1
+            while (k < K) {
+                const int kn = k + nch * 32;
+                if (kn < K) load_row(kn, nr, ni, nna);
+                drain_bin<true>(ar, ai, na, k, ev, ps, tab_c64, pol_keep, bestP, spec_row, gc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ar[i] = nr[i]; ai[i] = ni[i]; }
+                na = nna;
+                k = kn;
+            }
+        } else {
+#pragma unroll 1
+            while (k < K) {
+                const int kn = k + nch * 32;
+                if (kn < K) load_row(kn, nr, ni, nna);
+                drain_bin<false>(ar, ai, na, k, ev, ps, tab_c64, pol_keep, bestP, spec_row, gc);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ar[i] = nr[i]; ai[i] = ni[i]; }
+                na = nna;
+                k = kn;
+            }
         }
         __syncwarp();
         if (TRACE && dbg_cta && __activemask() != 0xffffffffu) ++ndiv1;  // (... and at the merge?)
@@ -522,7 +558,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
                     const int mma_fin_max /* no tensor-core pass starts once the window tickets have run out and this many covariance warps are done (0: once the tickets have run out); < 0: never any */,
                     const unsigned idle_ns /* sleep of a drain worker that found no unit */,
                     const int nch /* drain units per group, 1..FZ_NCH */,
-                    const int early_drain /* finished covariance warps start draining as soon as the tickets have run out, beside the tensor-core passes */)
+                    const int early_drain /* finished covariance warps start draining as soon as the tickets have run out, beside the tensor-core passes */,
+                    float *__restrict__ spec /* optional spectrum port [W][K] (float): every window then goes through the fp64 drain workers, which write it */)
 {
     long long *const dbg = TRACE ? dbg_in : nullptr;
     // programmatic dependent launch: the next launch on this stream may take the SMs this grid leaves (it needs a whole
@@ -547,7 +584,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
     if (threadIdx.x == 0) {
         if (dbg) { dbg[blockIdx.x * FZ_TRACE + 22] = 0; for (int i = 24; i < 30; ++i) dbg[blockIdx.x * FZ_TRACE + i] = 0; }  // (accumulated by the drain workers)
         ctl->cov_seq = 0; ctl->lock = 0; ctl->eig_done = 0; ctl->scan_done = 0; ctl->cov_finished = 0;
-        ctl->batch_start = 0; ctl->batch_cnt = 0; ctl->claim = 0; ctl->tout = 0; ctl->mma_off = mma_fin_max < 0 ? 1u : 0u;
+        ctl->batch_start = 0; ctl->batch_cnt = 0; ctl->claim = 0; ctl->tout = 0; ctl->mma_off = (mma_fin_max < 0 || spec != nullptr) ? 1u : 0u;
         ctl->dg_open = -1; ctl->drained_windows = 0; ctl->drain_groups = 0;
         const uint32_t tb0 = smem_u32(fz_smem + FZ_OFF_TBAR);
         for (int s = 0; s < FZ_TS; ++s) {
@@ -699,7 +736,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             if (dbg && fin == 0) dbg[blockIdx.x * FZ_TRACE + 1] = clock64() - t_start;                           // first one
         }
         __syncwarp();
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0, eig_jacobi = 0;
@@ -743,7 +780,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 10] = eig_rounds;
             dbg[blockIdx.x * FZ_TRACE + 19] = eig_jacobi;
         }
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else {
         // ================= scan warps =================
         const int st = threadIdx.x - 32 * (FZ_COV_WARPS + 1);  // 0..223
@@ -1079,7 +1116,7 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 3] = (long long)(g_end - g_start);   // ns, this CTA's lifetime (overwrites covariance warp 3's slot)
             dbg[blockIdx.x * FZ_TRACE + 2] = (long long)g_start;             // ns, absolute start (overwrites covariance warp 2's slot)
         }
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     }
     // The last CTA to finish re-arms the ticket counter for the next launch (launches of one handle are
     // serialised by the host, and by now every covariance warp has drawn a ticket >= W).

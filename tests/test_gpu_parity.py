@@ -331,6 +331,47 @@ def test_fused_kernel_degenerate_windows_take_the_jacobi_fallback():
     assert np.array_equal(got["bins"][ok], ref["bins"][ok])
 
 
+def test_fused_kernel_spectrum_port_matches_three_kernel_path(monkeypatch):
+    """Port 2 connected (/root/reference/lib/baz_music_doa.cc:120-121) on the fused M = 4 kernel: every window goes through the
+    fp64 drain workers, which write (float)P[k]; against the three-kernel path (bins and angles identical, spectrum and
+    levels to 1e-9: different eigensolvers) and the oracle, with degenerate windows and window counts that leave partial groups."""
+    cfg = synth.config(2)
+    table = helpers.table_for(cfg)
+    W = 333
+    x = synth.gen_windows_numpy(cfg, 4242, 0, W)
+    rng = np.random.default_rng(9)
+    x[3] = (rng.standard_normal(x.shape[1]) + 1j * rng.standard_normal(x.shape[1])).astype(np.complex64)  # noise only
+    x[5] = 0
+    x[17] *= np.float32(2.0 ** -60)
+    for nw in (W, 9, 1):
+        monkeypatch.setenv("MUSIC_B200_FUSED_SPEC", "1")
+        got = run_block(cfg, table, x[:nw], spectrum=True, device_path=True)
+        monkeypatch.setenv("MUSIC_B200_FUSED_SPEC", "0")
+        ref = run_block(cfg, table, x[:nw], spectrum=True, device_path=True)
+        assert got["launches"] < ref["launches"]  # table preparation + ONE launch
+        cmp = np.arange(nw) != 5  # (all-zero window: a flat spectrum whose argmax is decided by the last bit of either formula)
+        assert np.array_equal(got["bins"][cmp], ref["bins"][cmp]) and np.array_equal(got["angles"][cmp], ref["angles"][cmp])
+        ok = np.isfinite(ref["spectrum"]).all(axis=1)
+        assert ok.sum() >= nw - 1
+        assert helpers.rel_err(got["spectrum"][ok], ref["spectrum"][ok].astype(np.float64)) <= 1e-6  # float32 outputs
+        assert helpers.rel_err(got["levels"][ok], ref["levels"][ok]) <= 1e-6
+    monkeypatch.setenv("MUSIC_B200_FUSED_SPEC", "1")
+    sub = x[:24]
+    oracle = co.work_batch(sub, 4, 1, table, want_spectrum=True)
+    got = run_block(cfg, table, sub, spectrum=True, device_path=True)
+    okw = np.arange(24) != 5  # (the all-zero window has no defined eigenvectors)
+    assert np.array_equal(got["bins"][okw], oracle["bins"][okw])
+    assert helpers.rel_err(got["spectrum"][okw], oracle["P"][okw]) <= P_RTOL
+    # a NaN window: untouched initial pair (angle 0, level 0, bin -1), NaN spectrum row, neighbours unaffected
+    sub = sub.copy()
+    sub[7, 100] = np.nan
+    got = run_block(cfg, table, sub, spectrum=True, device_path=True)
+    assert got["bins"][7, 0] == -1 and got["angles"][7, 0] == 0.0 and got["levels"][7, 0] == 0.0
+    assert np.isnan(got["spectrum"][7]).all()
+    keep = okw & (np.arange(24) != 7)
+    assert np.array_equal(got["bins"][keep], oracle["bins"][keep])
+
+
 @pytest.mark.parametrize("base,over", [(4, {}), (3, {"snapshots": 1000, "resolution": 777}), (4, {"snapshots": 130, "snr_db": 0.0})])
 def test_fused_m8_kernel_matches_unfused_path_and_oracle(monkeypatch, base, over):
     """M = 8, n = 1, peak outputs: the fused persistent kernel (music_fused8.cuh) against the three-kernel path on every
