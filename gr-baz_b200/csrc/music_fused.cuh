@@ -357,7 +357,7 @@ __device__ __forceinline__ void fused_retire(unsigned char *smem, const unsigned
 // CTA's very last windows; its FZ_NCH units interleave the table in steps of 32 bins (unit c: bins (i * FZ_NCH + c) * 32
 // + lane, i = 0, 1, ..), the next row is requested before the current one is evaluated.  Returns the number of units
 // this warp processed.
-template <bool TRACE>
+template <bool TRACE, bool SPEC>
 __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float *__restrict__ tab_c64, const unsigned idle_ns, const int nch, const int early_drain, const int K,
                                                float *__restrict__ spec /* [W][K] or null */, const PeakOut out, long long *__restrict__ dbg_in, const long long t_start)
 {
@@ -455,8 +455,8 @@ __device__ __noinline__ int fused_drain_worker(unsigned char *smem, const float 
         double bestP[FZ_DG] = {0.0, 0.0, 0.0, 0.0};
         float *spec_row[FZ_DG];
 #pragma unroll
-        for (int b = 0; b < FZ_DG; ++b) spec_row[b] = spec ? spec + (size_t)qwin[(gs + (unsigned)min(b, gc - 1)) % FZ_Q] * K : nullptr;
-        if (spec) {
+        for (int b = 0; b < FZ_DG; ++b) spec_row[b] = SPEC ? spec + (size_t)qwin[(gs + (unsigned)min(b, gc - 1)) % FZ_Q] * K : nullptr;
+        if (SPEC) {  // (compile time: the default instantiation carries neither the strengths nor the row pointers)
 #pragma unroll 1
             while (k < K) {
                 const int kn = k + nch * 32;
@@ -736,7 +736,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             if (dbg && fin == 0) dbg[blockIdx.x * FZ_TRACE + 1] = clock64() - t_start;                           // first one
         }
         __syncwarp();
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        if (spec) fused_drain_worker<TRACE, true>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        else fused_drain_worker<TRACE, false>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, nullptr, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else if (warp == FZ_COV_WARPS) {
         // ================= eigensolver warp =================
         long long eig_busy = 0, eig_rounds = 0, eig_jacobi = 0;
@@ -780,7 +781,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 10] = eig_rounds;
             dbg[blockIdx.x * FZ_TRACE + 19] = eig_jacobi;
         }
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        if (spec) fused_drain_worker<TRACE, true>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        else fused_drain_worker<TRACE, false>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, nullptr, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     } else {
         // ================= scan warps =================
         const int st = threadIdx.x - 32 * (FZ_COV_WARPS + 1);  // 0..223
@@ -1116,7 +1118,8 @@ music4_fused_kernel(const float *__restrict__ in, const PlanarStreams S, unsigne
             dbg[blockIdx.x * FZ_TRACE + 3] = (long long)(g_end - g_start);   // ns, this CTA's lifetime (overwrites covariance warp 3's slot)
             dbg[blockIdx.x * FZ_TRACE + 2] = (long long)g_start;             // ns, absolute start (overwrites covariance warp 2's slot)
         }
-        fused_drain_worker<TRACE>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        if (spec) fused_drain_worker<TRACE, true>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, spec, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
+        else fused_drain_worker<TRACE, false>(fz_smem, tab_c64, idle_ns, nch, early_drain, K, nullptr, out, dbg ? dbg + blockIdx.x * FZ_TRACE : nullptr, t_start);
     }
     // The last CTA to finish re-arms the ticket counter for the next launch (launches of one handle are
     // serialised by the host, and by now every covariance warp has drawn a ticket >= W).
