@@ -200,6 +200,10 @@ int music_b200_process_host(music_b200 *h, const float *in_c64, uint32_t nwindow
  * benchmark path, and the entry a device-resident upstream block would call).  Enqueued on
  * `stream` (a cudaStream_t, NULL = legacy default stream); does not synchronise.
  * d_in must be 16-byte aligned.
+ * m = 4, n = 1 (and m = 8, n = 1 without the spectrum) run as ONE persistent kernel per call; consecutive calls of the
+ * m = 4 kernel on one stream overlap their launch tails (programmatic dependent launch) while their results still
+ * land in stream order.  d_spectrum != NULL (reference :120-121) keeps m = 4 / n = 1 on that kernel (its fp64 workers
+ * write the spectrum); other shapes then take the three-kernel path.
  */
 int music_b200_process_device(music_b200 *h, const float *d_in_c64, uint32_t nwindows,
                               float *d_angles, float *d_levels, float *d_spectrum,
