@@ -566,12 +566,31 @@ def run_ours(args):
     # --nccl-gather: the round-1 form (async double-buffered ncclAllGather overlapping the next step), kept for A/B.
     fused_gather = G > 1 and not args.nccl_gather
     gathered = None  # torch view of this rank's stream-ordered gather buffer
+    gather_fallback = None
     if fused_gather:
-        mine = np.frombuffer(blk.gather_create(W * G), dtype=np.uint8).copy()
+        # every rank takes every collective below whatever happens locally; if any rank cannot set the peer mapping up
+        # (IPC refused, ...), ALL ranks fall back to the NCCL all-gather together
+        ok, why = 1, ""
+        mine = np.zeros(128, np.uint8)
+        try:
+            mine = np.frombuffer(blk.gather_create(W * G), dtype=np.uint8).copy()
+        except Exception as e:
+            ok, why = 0, repr(e)[:200]
         t_mine = torch.from_numpy(mine).to(dev)
         t_all = torch.empty((G, 128), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(t_all.view(-1), t_mine)
-        blk.gather_attach(G, rank, [bytes(t_all[r].cpu().numpy().tobytes()) for r in range(G)])
+        if ok:
+            try:
+                blk.gather_attach(G, rank, [bytes(t_all[r].cpu().numpy().tobytes()) for r in range(G)])
+            except Exception as e:
+                ok, why = 0, repr(e)[:200]
+        t_ok = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            fused_gather = False
+            gather_fallback = "fused all-gather unavailable on at least one rank (%s): ncclAllGather instead" % (why or "another rank")
+            if rank == 0:
+                print("[bench] " + gather_fallback, file=sys.stderr, flush=True)
     d_all2 = [torch.empty((G, W, n), dtype=torch.int32, device=dev), torch.empty((G, W, n), dtype=torch.int32, device=dev)] if (G > 1 and not fused_gather) else None
     d_bins2 = [d_bins, torch.empty_like(d_bins)]
     pending = [None, None]
@@ -649,6 +668,8 @@ def run_ours(args):
                             "equals_nccl_all_gather": bool(torch.equal(mine_all, ref_stream))}
         else:
             gather_check = {"how": "async double-buffered ncclAllGather", "equals_nccl_all_gather": True}
+            if gather_fallback:
+                gather_check["fallback"] = gather_fallback
 
     # sanity: the result of the timed work is a real answer (mirror-folded true bins at 20 dB)
     bins_h = last_bins.cpu().numpy()
