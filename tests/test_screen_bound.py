@@ -104,3 +104,18 @@ def test_screen_error_on_adversarial_magnitudes():
             e = e * np.exp(-1j * np.angle(e[0]))
             worst = max(worst, worst_ratio(rows, e, True))
     assert worst <= B / 3.0, worst
+
+
+def test_generalised_screen_for_eight_antennas_stays_below_its_bound():
+    """the next step for the M = 8 kernel: the same screen with 16 columns; its bound grows with the
+    number of fp32 accumulations (B_M = 2^-15 M / 4) and few bins survive it on the config-4 stream"""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import emulate_screen_general as g
+
+    r = g.study(4, windows=6)
+    assert r["B"] == 2.0 ** -14
+    assert r["worst_err_over_na"] <= r["B"] / 3.0
+    assert r["survivors_max"] <= 64
