@@ -5,8 +5,8 @@
 //   warps 0..7   covariance (FP64 pipe): per-warp TMA ring exactly as cov4_tma_kernel; a finished
 //                window's R is written to a 64-slot shared-memory queue and marked ready (per-slot flag).
 //   warp  8      eigenvectors, four lanes per queued window (8 windows per round): principal eigenvector by
-//                repeated squaring + Householder basis of its complement (music_eig4p.cuh, ~2 k cycles per
-//                round); windows that do not converge (noise only, NaN) go through the full Jacobi solver
+//                repeated squaring + Householder basis of its complement (music_eig4p.cuh; 7.5 k cycles per
+//                round under the covariance warps' FP64 load); windows that do not converge (noise only, NaN) go through the full Jacobi solver
 //                (herm_eig4_coop in music_kernels.cuh, ~26 k cycles), which MUSIC_B200_EIG=jacobi selects for all.
 //   warps 9..15  pseudospectrum scan + peak pick, 8 windows per pass (two sweeps of the table):
 //                  1. SCREEN on the tensor cores: c_k = e_s^H a_k for all bins k and the 4 windows as a
